@@ -1,0 +1,209 @@
+# -*- coding: utf-8 -*-
+"""ctypes binding of libgravb200.so (include/gravb200.h).
+
+This is the only way Python reaches the CUDA code.  There is no fallback of any kind: if the shared
+library is missing `load()` raises, and if it cannot find an sm_100 device every compute call raises
+`GravB200Error` with the library's own message.
+
+The binding mirrors how the reference binds its native kernels
+(/root/reference/src/gravitation/kernel/c4b.py:86-93: `ctypes.cdll.LoadLibrary(.../lib.so)` + argtypes).
+"""
+
+import ctypes
+import os
+
+import numpy as np
+
+F32, F64 = 0, 1
+NCCL_ID_BYTES = 128
+_DTYPES = {'float32': F32, 'float64': F64}
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libgravb200.so')
+
+# every symbol include/gravb200.h declares: (name, restype, argtypes)
+_c_ctx = ctypes.c_void_p
+_SIGNATURES = [
+	('gravb200_abi_version', ctypes.c_int, []),
+	('gravb200_device_count', ctypes.c_int, []),
+	('gravb200_last_error', ctypes.c_char_p, []),
+	('gravb200_ctx_create', ctypes.c_int, [
+		ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+		ctypes.c_void_p, ctypes.POINTER(_c_ctx),
+		]),
+	('gravb200_ctx_destroy', ctypes.c_int, [_c_ctx]),
+	('gravb200_nccl_unique_id', ctypes.c_int, [ctypes.c_void_p]),
+	('gravb200_upload', ctypes.c_int, [
+		_c_ctx, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+		ctypes.c_double, ctypes.c_double, ctypes.c_double,
+		]),
+	('gravb200_upload_positions', ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
+	('gravb200_stage1', ctypes.c_int, [_c_ctx]),
+	('gravb200_stage2', ctypes.c_int, [_c_ctx]),
+	('gravb200_steps', ctypes.c_int, [_c_ctx, ctypes.c_int]),
+	('gravb200_sync', ctypes.c_int, [_c_ctx]),
+	('gravb200_download', ctypes.c_int, [_c_ctx, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+	('gravb200_shard', ctypes.c_int, [_c_ctx, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
+	('gravb200_timings', ctypes.c_int, [_c_ctx, ctypes.POINTER(ctypes.c_float), ctypes.c_int]),
+	('gravb200_info', ctypes.c_int, [_c_ctx, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
+	('gravb200_set_variant', ctypes.c_int, [_c_ctx, ctypes.c_int]),
+	('gravb200_variant_count', ctypes.c_int, [ctypes.c_int]),
+	('gravb200_variant_name', ctypes.c_char_p, [ctypes.c_int, ctypes.c_int]),
+	('gravb200_device_ptr', ctypes.c_void_p, [_c_ctx, ctypes.c_int]),
+	('gravb200_peak_probe', ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_int]),
+	]
+SYMBOLS = tuple(name for name, _, _ in _SIGNATURES)
+
+_lib = None
+
+
+class GravB200Error(RuntimeError):
+	"""a libgravb200 call returned a negative status"""
+
+
+def load():
+	"""dlopen libgravb200.so and declare every prototype; raises if the library was not built"""
+	global _lib
+	if _lib is not None:
+		return _lib
+	if not os.path.isfile(LIB_PATH):
+		raise GravB200Error(
+			'%s not found: build it with `make -C gravitation_b200/csrc` '
+			'(or `python -c "import __graft_entry__ as g; g.build()"`). There is no CPU fallback.' % LIB_PATH
+			)
+	lib = ctypes.CDLL(LIB_PATH, mode = ctypes.RTLD_GLOBAL)
+	for name, restype, argtypes in _SIGNATURES:
+		fn = getattr(lib, name) # AttributeError if the symbol is missing
+		fn.restype = restype
+		fn.argtypes = argtypes
+	_lib = lib
+	return lib
+
+
+def _check(rc):
+	if rc != 0:
+		raise GravB200Error('libgravb200: %s (code %d)' % (_lib.gravb200_last_error().decode('utf-8', 'replace'), rc))
+
+
+def device_count():
+	return load().gravb200_device_count()
+
+
+def nccl_unique_id():
+	buf = ctypes.create_string_buffer(NCCL_ID_BYTES)
+	_check(load().gravb200_nccl_unique_id(buf))
+	return buf.raw
+
+
+def peak_probe(device = 0):
+	"""measured non-tensor peaks: dict(fp32_tflops, fp32x2_tflops, fp64_tflops, mufu_gops, sm_mhz)"""
+	out = (ctypes.c_double * 5)()
+	_check(load().gravb200_peak_probe(device, out, 5))
+	return dict(fp32_tflops = out[0], fp32x2_tflops = out[1], fp64_tflops = out[2], mufu_gops = out[3], sm_mhz = out[4])
+
+
+def variant_names(dtype = 'float32'):
+	lib = load()
+	d = _DTYPES[dtype]
+	return [lib.gravb200_variant_name(d, i).decode() for i in range(lib.gravb200_variant_count(d))]
+
+
+def _ptr(a):
+	return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+class Shard:
+	"""one GPU's share of a universe: thin object wrapper over gravb200_ctx"""
+
+	def __init__(self, n_total, dtype = 'float32', device = 0, rank = 0, world = 1, nccl_id = None):
+		self._lib = load()
+		self._np = np.dtype(dtype)
+		self.n_total = int(n_total)
+		self.dtype = dtype
+		self.rank, self.world = rank, world
+		ctx = _c_ctx()
+		idbuf = None
+		if nccl_id is not None:
+			idbuf = ctypes.create_string_buffer(bytes(nccl_id), NCCL_ID_BYTES)
+		_check(self._lib.gravb200_ctx_create(
+			self.n_total, _DTYPES[dtype], device, rank, world, idbuf, ctypes.byref(ctx),
+			))
+		self._ctx = ctx
+		row0, n_local = ctypes.c_int64(), ctypes.c_int64()
+		_check(self._lib.gravb200_shard(self._ctx, ctypes.byref(row0), ctypes.byref(n_local)))
+		self.row0, self.n_local = row0.value, n_local.value
+
+	def _arr(self, a, shape):
+		a = np.ascontiguousarray(a, dtype = self._np)
+		if a.shape != shape:
+			raise ValueError('expected shape %s, got %s' % (shape, a.shape))
+		return a
+
+	def upload(self, r, v, m, G, T, eps = 0.0):
+		r = self._arr(r, (self.n_total, 3))
+		v = self._arr(v, (self.n_total, 3))
+		m = self._arr(m, (self.n_total,))
+		_check(self._lib.gravb200_upload(self._ctx, _ptr(r), _ptr(v), _ptr(m), G, T, eps))
+
+	def upload_positions(self, r):
+		r = self._arr(r, (self.n_total, 3))
+		_check(self._lib.gravb200_upload_positions(self._ctx, _ptr(r)))
+
+	def upload_raw(self, r_ptr, v_ptr, m_ptr, G, T, eps = 0.0):
+		"""host pointers (ints) of C-contiguous buffers in the context dtype, e.g. pinned memory"""
+		_check(self._lib.gravb200_upload(self._ctx, r_ptr, v_ptr, m_ptr, G, T, eps))
+
+	def download_raw(self, r_ptr, v_ptr, a_ptr):
+		_check(self._lib.gravb200_download(self._ctx, r_ptr, v_ptr, a_ptr))
+
+	def stage1(self):
+		_check(self._lib.gravb200_stage1(self._ctx))
+
+	def stage2(self):
+		_check(self._lib.gravb200_stage2(self._ctx))
+
+	def steps(self, k):
+		_check(self._lib.gravb200_steps(self._ctx, int(k)))
+
+	def sync(self):
+		_check(self._lib.gravb200_sync(self._ctx))
+
+	def download(self, r = True, v = True, a = False, out_r = None, out_v = None, out_a = None):
+		"""returns (r[n_total,3] | None, v[n_local,3] | None, a[n_local,3] | None)"""
+		if r and out_r is None:
+			out_r = np.empty((self.n_total, 3), dtype = self._np)
+		if v and out_v is None:
+			out_v = np.empty((self.n_local, 3), dtype = self._np)
+		if a and out_a is None:
+			out_a = np.empty((self.n_local, 3), dtype = self._np)
+		_check(self._lib.gravb200_download(
+			self._ctx, _ptr(out_r if r else None), _ptr(out_v if v else None), _ptr(out_a if a else None),
+			))
+		return (out_r if r else None, out_v if v else None, out_a if a else None)
+
+	def timings(self):
+		ms = (ctypes.c_float * 3)()
+		_check(self._lib.gravb200_timings(self._ctx, ms, 3))
+		return dict(sweep_ms = ms[0], exchange_ms = ms[1], steps_ms = ms[2])
+
+	def info(self):
+		v = (ctypes.c_int64 * 10)()
+		_check(self._lib.gravb200_info(self._ctx, v, 10))
+		keys = ('grid', 'threads', 'bodies_per_thread', 'tile', 'stages', 'smem_bytes', 'launches', 'sm_count', 'packed', 'ctas_per_sm')
+		return dict(zip(keys, [int(x) for x in v]))
+
+	def set_variant(self, variant):
+		_check(self._lib.gravb200_set_variant(self._ctx, int(variant)))
+
+	def device_ptr(self, which):
+		return self._lib.gravb200_device_ptr(self._ctx, which)
+
+	def close(self):
+		if self._ctx is not None and self._ctx.value:
+			self._lib.gravb200_ctx_destroy(self._ctx)
+			self._ctx = None
+
+	def __del__(self):
+		try:
+			self.close()
+		except Exception:
+			pass

@@ -1,0 +1,758 @@
+// gravb200.cu — C-ABI shim (include/gravb200.h) around the sm_100a sweep kernel.
+//
+// The context owns every device allocation, the stream, the events and (multi-GPU) the NCCL
+// communicator.  There is deliberately no CPU implementation in this file: every compute entry
+// point needs a CUDA device and fails with GRAVB200_ECUDA / GRAVB200_ENODEV otherwise.
+//
+// Reference interfaces replaced (pleiszenburg/gravitation, src/gravitation/kernel/):
+//   start_kernel  pc2.py:96-145      -> gravb200_ctx_create + gravb200_upload
+//   step_stage1   pc2.py:147-162     -> gravb200_stage1   (no per-step H2D/D2H)
+//   step_stage2   np2.py:110-115     -> fused into the sweep epilogue; gravb200_stage2 commits
+//   stop_kernel   _base_.py:174-177  -> gravb200_ctx_destroy
+#include "../../include/gravb200.h"
+#include "nbody_kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only; the library is dlopen'ed so single-GPU use needs no NCCL
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace gravb200;
+
+namespace {
+
+thread_local char g_err[1024] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                             \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail(GRAVB200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                 \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// NCCL, resolved at run time
+// ---------------------------------------------------------------------------------------------
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool tried = false;
+};
+NcclApi g_nccl;
+
+int nccl_load() {
+    if (g_nccl.handle) return 0;
+    if (g_nccl.tried) return fail(GRAVB200_ENCCL, "NCCL library could not be loaded");
+    g_nccl.tried = true;
+    const char* names[] = {getenv("GRAVB200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        if (!nm || !*nm) continue;
+        g_nccl.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.handle) break;
+    }
+    if (!g_nccl.handle) return fail(GRAVB200_ENCCL, "dlopen(libnccl.so.2) failed: %s", dlerror());
+#define SYM(field, name)                                                          \
+    *(void**)(&g_nccl.field) = dlsym(g_nccl.handle, name);                        \
+    if (!g_nccl.field) return fail(GRAVB200_ENCCL, "NCCL symbol %s missing", name)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(AllGather, "ncclAllGather");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    return 0;
+}
+#define NC(call)                                                                           \
+    do {                                                                                   \
+        ncclResult_t r_ = (call);                                                          \
+        if (r_ != ncclSuccess)                                                             \
+            return fail(GRAVB200_ENCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Kernel variants
+// ---------------------------------------------------------------------------------------------
+struct Variant {
+    const char* name;
+    int threads, r, tile, stages, minb, pack;
+    size_t smem;
+    const void* fn;
+};
+
+template <typename REAL, int THREADS, int R, int TILE, int STAGES, int MINB, int PACK>
+Variant make_variant(const char* name) {
+    Variant v;
+    v.name = name;
+    v.threads = THREADS; v.r = R; v.tile = TILE; v.stages = STAGES; v.minb = MINB; v.pack = PACK;
+    v.smem = sweep_smem_bytes<REAL, THREADS, R, TILE, STAGES>();
+    v.fn = (const void*)&sweep_kernel<REAL, THREADS, R, TILE, STAGES, MINB, PACK>;
+    return v;
+}
+
+// Ordered large -> small work granularity; the automatic choice takes the first one that still
+// gives every resident CTA >= 8 tiles (see pick_variant).  Entries after the "auto" prefix are
+// only reachable through gravb200_set_variant (ncu A/B evidence, tuning sweeps).
+#define V32(T, R, TILE, ST, MB, PK) \
+    make_variant<float, T, R, TILE, ST, MB, PK>("f32_t" #T "_r" #R "_j" #TILE "_s" #ST "_b" #MB "_p" #PK)
+#define V64(T, R, TILE, ST, MB) \
+    make_variant<double, T, R, TILE, ST, MB, 0>("f64_t" #T "_r" #R "_j" #TILE "_s" #ST "_b" #MB)
+
+const std::vector<Variant>& variants_f32() {
+    static const std::vector<Variant> v = {
+        V32(256, 8, 512, 3, 2, 1),   // 0  auto: large N
+        V32(256, 4, 256, 3, 2, 1),   // 1  auto
+        V32(128, 4, 128, 3, 4, 1),   // 2  auto
+        V32(128, 2, 64, 4, 4, 1),    // 3  auto: tiny N
+        V32(256, 8, 512, 3, 2, 0),   // 4  scalar-FFMA twin of 0 (A/B)
+        V32(256, 4, 256, 3, 2, 0),   // 5  scalar-FFMA twin of 1
+        V32(128, 8, 512, 3, 4, 1),   // 6
+        V32(256, 8, 256, 4, 2, 1),   // 7
+        V32(256, 8, 1024, 2, 2, 1),  // 8
+        V32(512, 4, 512, 3, 1, 1),   // 9
+        V32(256, 6, 512, 3, 2, 1),   // 10
+        V32(256, 12, 512, 3, 1, 1),  // 11
+        V32(128, 8, 512, 3, 2, 1),   // 12
+        V32(256, 8, 512, 3, 1, 1),   // 13
+    };
+    return v;
+}
+constexpr int kAutoF32 = 4;
+
+const std::vector<Variant>& variants_f64() {
+    static const std::vector<Variant> v = {
+        V64(256, 4, 256, 3, 2),   // 0 auto: large N
+        V64(128, 2, 128, 3, 4),   // 1 auto
+        V64(128, 1, 64, 4, 4),    // 2 auto: tiny N
+        V64(256, 2, 256, 3, 2),   // 3
+        V64(128, 4, 256, 3, 4),   // 4
+        V64(256, 6, 256, 3, 1),   // 5
+    };
+    return v;
+}
+constexpr int kAutoF64 = 3;
+
+// ---------------------------------------------------------------------------------------------
+// O(N) helper kernels: layout conversion between the reference's (N,3)+(N,) host arrays
+// (np2.py:63-66) and the device float4/double4 state.
+// ---------------------------------------------------------------------------------------------
+template <typename REAL, typename V4>
+__global__ void pack_rm_kernel(const REAL* __restrict__ r3, const REAL* __restrict__ m, V4* out, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V4 o;
+    o.x = r3[3 * i]; o.y = r3[3 * i + 1]; o.z = r3[3 * i + 2];
+    o.w = m ? m[i] : out[i].w;
+    out[i] = o;
+}
+template <typename REAL, typename V4>
+__global__ void pack_v_kernel(const REAL* __restrict__ v3, V4* out, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V4 o;
+    o.x = v3[3 * i]; o.y = v3[3 * i + 1]; o.z = v3[3 * i + 2]; o.w = 0;
+    out[i] = o;
+}
+template <typename REAL, typename V4>
+__global__ void unpack_kernel(const V4* __restrict__ in, REAL* out3, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V4 v = in[i];
+    out3[3 * i] = v.x; out3[3 * i + 1] = v.y; out3[3 * i + 2] = v.z;
+}
+
+}  // namespace
+
+struct gravb200_ctx {
+    int dtype = 0, device = 0, rank = 0, world = 1;
+    size_t esz = 4;            // sizeof(REAL)
+    int64_t n_total = 0, chunk = 0, n_pad = 0, row0 = 0, n_local = 0;
+    double G = 0, T = 0, eps = 0;
+    bool uploaded = false, pending = false;   // pending: stage1 issued, stage2 not yet
+    int front = 0;
+    void* pos[2] = {nullptr, nullptr};
+    void* vel[2] = {nullptr, nullptr};
+    void* acc = nullptr;
+    double* partial = nullptr;
+    size_t partial_bytes = 0;
+    unsigned int* counters = nullptr;
+    size_t counters_n = 0;
+    void* stage3 = nullptr;     // device staging for (N,3) host arrays
+    void* stagem = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ev_sweep = false, ev_xchg = false, ev_steps = false;
+    ncclComm_t comm = nullptr;
+    int sm_count = 0;
+    int forced_variant = -1;
+    int variant = 0, grid = 0, occ = 0;
+    int64_t launches = 0;
+};
+
+namespace {
+
+const std::vector<Variant>& variants_of(int dtype) {
+    return dtype == GRAVB200_F32 ? variants_f32() : variants_f64();
+}
+
+int occupancy_of(const Variant& v, int* occ) {
+    CU(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, v.fn, v.threads, v.smem));
+    if (*occ < 1) return fail(GRAVB200_ECUDA, "variant %s does not fit on an SM", v.name);
+    return 0;
+}
+
+long long tiles_of(const gravb200_ctx* c, const Variant& v) {
+    const long long iblk = (long long)v.threads * v.r;
+    const long long nib = (c->n_local + iblk - 1) / iblk;
+    const long long njt = (c->n_total + v.tile - 1) / v.tile;
+    return nib * njt;
+}
+
+// choose the variant and size its workspace
+int pick_variant(gravb200_ctx* c) {
+    const auto& vs = variants_of(c->dtype);
+    const int n_auto = c->dtype == GRAVB200_F32 ? kAutoF32 : kAutoF64;
+    int pick = n_auto - 1, occ = 0;
+    if (c->forced_variant >= 0) {
+        pick = c->forced_variant;
+        int rc = occupancy_of(vs[pick], &occ);
+        if (rc) return rc;
+    } else {
+        for (int i = 0; i < n_auto; ++i) {
+            int rc = occupancy_of(vs[i], &occ);
+            if (rc) return rc;
+            if (tiles_of(c, vs[i]) >= 8LL * occ * c->sm_count) { pick = i; break; }
+        }
+        int rc = occupancy_of(vs[pick], &occ);
+        if (rc) return rc;
+    }
+    const Variant& v = vs[pick];
+    const long long total = tiles_of(c, v);
+    long long grid = (long long)occ * c->sm_count;
+    if (grid > total) grid = total;
+    c->variant = pick;
+    c->occ = occ;
+    c->grid = (int)grid;
+    const long long iblk = (long long)v.threads * v.r;
+    const size_t need = (size_t)2 * (size_t)std::max<long long>(grid, 1) * iblk * 4 * sizeof(double);
+    if (need > c->partial_bytes) {
+        if (c->partial) CU(cudaFree(c->partial));
+        c->partial = nullptr;
+        CU(cudaMalloc(&c->partial, need));
+        c->partial_bytes = need;
+    }
+    const size_t nib = (size_t)((c->n_local + iblk - 1) / iblk);
+    if (nib > c->counters_n) {
+        if (c->counters) CU(cudaFree(c->counters));
+        c->counters = nullptr;
+        CU(cudaMalloc(&c->counters, std::max<size_t>(nib, 1) * sizeof(unsigned int)));
+        c->counters_n = nib;
+    }
+    if (c->counters_n) CU(cudaMemsetAsync(c->counters, 0, c->counters_n * sizeof(unsigned int), c->stream));
+    return 0;
+}
+
+int launch_sweep(gravb200_ctx* c, int integrate) {
+    if (c->n_local <= 0 || c->grid <= 0) return 0;
+    const Variant& v = variants_of(c->dtype)[c->variant];
+    SweepParams p;
+    p.pos_front = c->pos[c->front];
+    p.pos_back = c->pos[c->front ^ 1];
+    p.vel_front = c->vel[c->front];
+    p.vel_back = c->vel[c->front ^ 1];
+    p.acc = c->acc;
+    p.partial = c->partial;
+    p.counters = c->counters;
+    p.n_total = c->n_total;
+    p.row0 = c->row0;
+    p.n_local = c->n_local;
+    const long long iblk = (long long)v.threads * v.r;
+    p.n_iblocks = (int)((c->n_local + iblk - 1) / iblk);
+    p.n_jtiles = (int)((c->n_total + v.tile - 1) / v.tile);
+    p.G = c->G;
+    p.T = c->T;
+    p.eps2_f = (float)(c->eps * c->eps);
+    p.eps2_d = c->eps * c->eps;
+    p.integrate = integrate;
+    void* args[] = {&p};
+    CU(cudaLaunchKernel(v.fn, dim3(c->grid), dim3(v.threads), args, v.smem, c->stream));
+    c->launches++;
+    return 0;
+}
+
+int exchange(gravb200_ctx* c) {
+    if (c->world == 1) return 0;
+    char* back = (char*)c->pos[c->front ^ 1];
+    const size_t count = (size_t)c->chunk * 4;   // scalars per shard
+    NC(g_nccl.AllGather(back + (size_t)c->rank * c->chunk * 4 * c->esz, back, count,
+                        c->dtype == GRAVB200_F32 ? ncclFloat32 : ncclFloat64, c->comm, c->stream));
+    return 0;
+}
+
+template <typename REAL, typename V4>
+int upload_impl(gravb200_ctx* c, const void* r, const void* v, const void* m) {
+    const long long n = c->n_total;
+    const int tb = 256;
+    const unsigned gb = (unsigned)((n + tb - 1) / tb);
+    if (r) {
+        CU(cudaMemcpyAsync(c->stage3, r, (size_t)n * 3 * sizeof(REAL), cudaMemcpyHostToDevice, c->stream));
+        if (m) CU(cudaMemcpyAsync(c->stagem, m, (size_t)n * sizeof(REAL), cudaMemcpyHostToDevice, c->stream));
+        pack_rm_kernel<REAL, V4><<<gb, tb, 0, c->stream>>>((const REAL*)c->stage3, m ? (const REAL*)c->stagem : nullptr,
+                                                          (V4*)c->pos[c->front], n);
+        CU(cudaGetLastError());
+        c->launches++;
+    }
+    if (v && c->n_local > 0) {
+        // only this shard's rows are kept
+        const REAL* vsrc = (const REAL*)v + (size_t)c->row0 * 3;
+        CU(cudaMemcpyAsync(c->stage3, vsrc, (size_t)c->n_local * 3 * sizeof(REAL), cudaMemcpyHostToDevice, c->stream));
+        const unsigned gl = (unsigned)((c->n_local + tb - 1) / tb);
+        pack_v_kernel<REAL, V4><<<gl, tb, 0, c->stream>>>((const REAL*)c->stage3, (V4*)c->vel[c->front], c->n_local);
+        CU(cudaGetLastError());
+        c->launches++;
+    }
+    return 0;
+}
+
+template <typename REAL, typename V4>
+int download_impl(gravb200_ctx* c, void* r, void* v, void* a) {
+    const int tb = 256;
+    if (r) {
+        const long long n = c->n_total;
+        unpack_kernel<REAL, V4><<<(unsigned)((n + tb - 1) / tb), tb, 0, c->stream>>>((const V4*)c->pos[c->front], (REAL*)c->stage3, n);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(r, c->stage3, (size_t)n * 3 * sizeof(REAL), cudaMemcpyDeviceToHost, c->stream));
+        c->launches++;
+    }
+    const long long nl = c->n_local;
+    if (v && nl > 0) {
+        unpack_kernel<REAL, V4><<<(unsigned)((nl + tb - 1) / tb), tb, 0, c->stream>>>((const V4*)c->vel[c->front], (REAL*)c->stage3, nl);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(v, c->stage3, (size_t)nl * 3 * sizeof(REAL), cudaMemcpyDeviceToHost, c->stream));
+        c->launches++;
+    }
+    if (a && nl > 0) {
+        unpack_kernel<REAL, V4><<<(unsigned)((nl + tb - 1) / tb), tb, 0, c->stream>>>((const V4*)c->acc, (REAL*)c->stage3, nl);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(a, c->stage3, (size_t)nl * 3 * sizeof(REAL), cudaMemcpyDeviceToHost, c->stream));
+        c->launches++;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// peak probe kernels (a measured non-tensor FP32/FP64 peak for the roofline)
+// ---------------------------------------------------------------------------------------------
+constexpr int kProbeIters = 4096;
+constexpr int kProbeChains = 8;
+
+__global__ void probe_ffma(float* out, float a, float b, unsigned long long* clk) {
+    float x[kProbeChains];
+#pragma unroll
+    for (int c = 0; c < kProbeChains; ++c) x[c] = (float)(threadIdx.x + c);
+    unsigned long long t0 = clock64(), g0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+    for (int i = 0; i < kProbeIters; ++i) {
+#pragma unroll
+        for (int c = 0; c < kProbeChains; ++c) x[c] = fmaf(x[c], a, b);
+    }
+    unsigned long long t1 = clock64(), g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    float s = 0;
+#pragma unroll
+    for (int c = 0; c < kProbeChains; ++c) s += x[c];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { clk[0] = t1 - t0; clk[1] = g1 - g0; }
+}
+__global__ void probe_ffma2(float* out, float a, float b) {
+    float2 x[kProbeChains];
+#pragma unroll
+    for (int c = 0; c < kProbeChains; ++c) x[c] = make_float2((float)(threadIdx.x + c), (float)c);
+    const float2 a2 = make_float2(a, a * 1.0001f), b2 = make_float2(b, b * 0.999f);
+    for (int i = 0; i < kProbeIters; ++i) {
+#pragma unroll
+        for (int c = 0; c < kProbeChains; ++c) x[c] = __ffma2_rn(x[c], a2, b2);
+    }
+    float s = 0;
+#pragma unroll
+    for (int c = 0; c < kProbeChains; ++c) s += x[c].x + x[c].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void probe_dfma(double* out, double a, double b) {
+    double x[kProbeChains];
+#pragma unroll
+    for (int c = 0; c < kProbeChains; ++c) x[c] = (double)(threadIdx.x + c);
+    for (int i = 0; i < kProbeIters; ++i) {
+#pragma unroll
+        for (int c = 0; c < kProbeChains; ++c) x[c] = fma(x[c], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < kProbeChains; ++c) s += x[c];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void probe_mufu(float* out) {
+    float x[kProbeChains];
+#pragma unroll
+    for (int c = 0; c < kProbeChains; ++c) x[c] = 1.5f + (float)(threadIdx.x + c);
+    for (int i = 0; i < kProbeIters; ++i) {
+#pragma unroll
+        for (int c = 0; c < kProbeChains; ++c) x[c] = rsqrt_approx(x[c]);
+    }
+    float s = 0;
+#pragma unroll
+    for (int c = 0; c < kProbeChains; ++c) s += x[c];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int gravb200_abi_version(void) { return 1; }
+
+const char* gravb200_last_error(void) { return g_err; }
+
+int gravb200_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        fail(GRAVB200_ENODEV, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        return 0;
+    }
+    return n;
+}
+
+int gravb200_variant_count(int dtype) {
+    if (dtype != GRAVB200_F32 && dtype != GRAVB200_F64) return 0;
+    return (int)variants_of(dtype).size();
+}
+const char* gravb200_variant_name(int dtype, int variant) {
+    if (dtype != GRAVB200_F32 && dtype != GRAVB200_F64) return "";
+    const auto& vs = variants_of(dtype);
+    if (variant < 0 || variant >= (int)vs.size()) return "";
+    return vs[variant].name;
+}
+
+int gravb200_nccl_unique_id(void* id) {
+    if (!id) return fail(GRAVB200_EINVAL, "id is NULL");
+    int rc = nccl_load();
+    if (rc) return rc;
+    static_assert(sizeof(ncclUniqueId) == GRAVB200_NCCL_ID_BYTES, "NCCL id size");
+    ncclUniqueId u;
+    NC(g_nccl.GetUniqueId(&u));
+    memcpy(id, &u, sizeof(u));
+    return 0;
+}
+
+int gravb200_ctx_create(int64_t n_total, int dtype, int device, int rank, int world, const void* nccl_id,
+                        gravb200_ctx** out) {
+    if (!out) return fail(GRAVB200_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (n_total < 1) return fail(GRAVB200_EINVAL, "n_total must be >= 1 (got %lld)", (long long)n_total);
+    if (dtype != GRAVB200_F32 && dtype != GRAVB200_F64) return fail(GRAVB200_EINVAL, "unknown dtype %d", dtype);
+    if (world < 1 || rank < 0 || rank >= world) return fail(GRAVB200_EINVAL, "bad rank/world %d/%d", rank, world);
+    if (world > 1 && !nccl_id) return fail(GRAVB200_EINVAL, "world > 1 needs an NCCL unique id");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(GRAVB200_ENODEV, "no CUDA device (%s); this library has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) return fail(GRAVB200_EINVAL, "device %d out of range [0,%d)", device, ndev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(GRAVB200_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+
+    gravb200_ctx* c = new (std::nothrow) gravb200_ctx();
+    if (!c) return fail(GRAVB200_EINVAL, "out of host memory");
+    c->dtype = dtype;
+    c->esz = dtype == GRAVB200_F32 ? 4 : 8;
+    c->device = device;
+    c->rank = rank;
+    c->world = world;
+    c->n_total = n_total;
+    c->chunk = (n_total + world - 1) / world;
+    c->n_pad = c->chunk * world;
+    c->row0 = std::min<int64_t>((int64_t)rank * c->chunk, n_total);
+    c->n_local = std::max<int64_t>(0, std::min<int64_t>(c->chunk, n_total - c->row0));
+    c->sm_count = prop.multiProcessorCount;
+
+    auto cleanup = [&](int rc) { gravb200_ctx_destroy(c); return rc; };
+#define CUX(call)                                                                                      \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return cleanup(fail(GRAVB200_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)));      \
+    } while (0)
+    CUX(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto& ev : c->ev) CUX(cudaEventCreate(&ev));
+    const size_t v4 = 4 * c->esz;
+    for (int b = 0; b < 2; ++b) {
+        CUX(cudaMalloc(&c->pos[b], (size_t)c->n_pad * v4));
+        CUX(cudaMemsetAsync(c->pos[b], 0, (size_t)c->n_pad * v4, c->stream));
+        CUX(cudaMalloc(&c->vel[b], (size_t)c->chunk * v4));
+        CUX(cudaMemsetAsync(c->vel[b], 0, (size_t)c->chunk * v4, c->stream));
+    }
+    CUX(cudaMalloc(&c->acc, (size_t)c->chunk * v4));
+    CUX(cudaMemsetAsync(c->acc, 0, (size_t)c->chunk * v4, c->stream));
+    CUX(cudaMalloc(&c->stage3, (size_t)n_total * 3 * c->esz));
+    CUX(cudaMalloc(&c->stagem, (size_t)n_total * c->esz));
+#undef CUX
+    if (world > 1) {
+        int rc = nccl_load();
+        if (rc) return cleanup(rc);
+        ncclUniqueId u;
+        memcpy(&u, nccl_id, sizeof(u));
+        ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, u, rank);
+        if (r != ncclSuccess)
+            return cleanup(fail(GRAVB200_ENCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)));
+    }
+    int rc = pick_variant(c);
+    if (rc) return cleanup(rc);
+    cudaError_t es = cudaStreamSynchronize(c->stream);
+    if (es != cudaSuccess) return cleanup(fail(GRAVB200_ECUDA, "init sync: %s", cudaGetErrorString(es)));
+    *out = c;
+    return 0;
+}
+
+int gravb200_ctx_destroy(gravb200_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (int b = 0; b < 2; ++b) {
+        if (c->pos[b]) cudaFree(c->pos[b]);
+        if (c->vel[b]) cudaFree(c->vel[b]);
+    }
+    if (c->acc) cudaFree(c->acc);
+    if (c->partial) cudaFree(c->partial);
+    if (c->counters) cudaFree(c->counters);
+    if (c->stage3) cudaFree(c->stage3);
+    if (c->stagem) cudaFree(c->stagem);
+    for (auto& ev : c->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int gravb200_upload(gravb200_ctx* c, const void* r, const void* v, const void* m, double G, double T, double eps) {
+    if (!c) return fail(GRAVB200_EINVAL, "ctx is NULL");
+    if (!r || !v || !m) return fail(GRAVB200_EINVAL, "r, v and m are required");
+    if (eps < 0) return fail(GRAVB200_EINVAL, "eps must be >= 0");
+    CU(cudaSetDevice(c->device));
+    c->G = G; c->T = T; c->eps = eps;
+    c->pending = false;
+    int rc = c->dtype == GRAVB200_F32 ? upload_impl<float, float4>(c, r, v, m) : upload_impl<double, double4>(c, r, v, m);
+    if (rc) return rc;
+    // masses travel in .w of both buffers: copy front -> back once so the epilogue's w is consistent
+    CU(cudaMemcpyAsync(c->pos[c->front ^ 1], c->pos[c->front], (size_t)c->n_pad * 4 * c->esz,
+                       cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->uploaded = true;
+    return 0;
+}
+
+int gravb200_upload_positions(gravb200_ctx* c, const void* r) {
+    if (!c || !r) return fail(GRAVB200_EINVAL, "ctx / r is NULL");
+    if (!c->uploaded) return fail(GRAVB200_EINVAL, "gravb200_upload must come first");
+    CU(cudaSetDevice(c->device));
+    c->pending = false;
+    int rc = c->dtype == GRAVB200_F32 ? upload_impl<float, float4>(c, r, nullptr, nullptr)
+                                      : upload_impl<double, double4>(c, r, nullptr, nullptr);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int gravb200_stage1(gravb200_ctx* c) {
+    if (!c) return fail(GRAVB200_EINVAL, "ctx is NULL");
+    if (!c->uploaded) return fail(GRAVB200_EINVAL, "no state uploaded");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    int rc = launch_sweep(c, 1);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev[1], c->stream));
+    c->ev_sweep = true;
+    c->pending = true;
+    return 0;
+}
+
+int gravb200_stage2(gravb200_ctx* c) {
+    if (!c) return fail(GRAVB200_EINVAL, "ctx is NULL");
+    if (!c->pending) return fail(GRAVB200_EINVAL, "stage2 without a preceding stage1");
+    CU(cudaSetDevice(c->device));
+    if (c->world > 1) {
+        CU(cudaEventRecord(c->ev[2], c->stream));
+        int rc = exchange(c);
+        if (rc) return rc;
+        CU(cudaEventRecord(c->ev[3], c->stream));
+        c->ev_xchg = true;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    c->front ^= 1;
+    c->pending = false;
+    return 0;
+}
+
+int gravb200_steps(gravb200_ctx* c, int k) {
+    if (!c) return fail(GRAVB200_EINVAL, "ctx is NULL");
+    if (!c->uploaded) return fail(GRAVB200_EINVAL, "no state uploaded");
+    if (k < 0) return fail(GRAVB200_EINVAL, "k < 0");
+    CU(cudaSetDevice(c->device));
+    c->pending = false;
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    for (int s = 0; s < k; ++s) {
+        int rc = launch_sweep(c, 1);
+        if (rc) return rc;
+        rc = exchange(c);
+        if (rc) return rc;
+        c->front ^= 1;
+    }
+    CU(cudaEventRecord(c->ev[1], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->ev_sweep = false;
+    c->ev_steps = true;
+    return 0;
+}
+
+int gravb200_sync(gravb200_ctx* c) {
+    if (!c) return fail(GRAVB200_EINVAL, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int gravb200_download(gravb200_ctx* c, void* r, void* v, void* a) {
+    if (!c) return fail(GRAVB200_EINVAL, "ctx is NULL");
+    if (!c->uploaded) return fail(GRAVB200_EINVAL, "no state uploaded");
+    CU(cudaSetDevice(c->device));
+    return c->dtype == GRAVB200_F32 ? download_impl<float, float4>(c, r, v, a) : download_impl<double, double4>(c, r, v, a);
+}
+
+int gravb200_shard(const gravb200_ctx* c, int64_t* row0, int64_t* n_local) {
+    if (!c) return fail(GRAVB200_EINVAL, "ctx is NULL");
+    if (row0) *row0 = c->row0;
+    if (n_local) *n_local = c->n_local;
+    return 0;
+}
+
+int gravb200_timings(gravb200_ctx* c, float* ms, int n) {
+    if (!c || !ms) return fail(GRAVB200_EINVAL, "ctx / ms is NULL");
+    CU(cudaSetDevice(c->device));
+    for (int i = 0; i < n; ++i) ms[i] = -1.f;
+    if (n > 0 && c->ev_sweep) CU(cudaEventElapsedTime(&ms[0], c->ev[0], c->ev[1]));
+    if (n > 1 && c->ev_xchg) CU(cudaEventElapsedTime(&ms[1], c->ev[2], c->ev[3]));
+    if (n > 2 && c->ev_steps) CU(cudaEventElapsedTime(&ms[2], c->ev[0], c->ev[1]));
+    return 0;
+}
+
+int gravb200_info(const gravb200_ctx* c, int64_t* info, int n) {
+    if (!c || !info) return fail(GRAVB200_EINVAL, "ctx / info is NULL");
+    const Variant& v = variants_of(c->dtype)[c->variant];
+    const int64_t vals[10] = {c->grid, v.threads, v.r, v.tile, v.stages, (int64_t)v.smem,
+                              c->launches, c->sm_count, v.pack, c->occ};
+    for (int i = 0; i < n && i < 10; ++i) info[i] = vals[i];
+    return 0;
+}
+
+int gravb200_set_variant(gravb200_ctx* c, int variant) {
+    if (!c) return fail(GRAVB200_EINVAL, "ctx is NULL");
+    if (variant >= (int)variants_of(c->dtype).size()) return fail(GRAVB200_EINVAL, "variant %d out of range", variant);
+    if (c->pending) return fail(GRAVB200_EINVAL, "cannot switch variant between stage1 and stage2");
+    CU(cudaSetDevice(c->device));
+    c->forced_variant = variant < 0 ? -1 : variant;
+    int rc = pick_variant(c);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+void* gravb200_device_ptr(gravb200_ctx* c, int which) {
+    if (!c) return nullptr;
+    switch (which) {
+        case 0: return c->pos[c->front];
+        case 1: return c->pos[c->front ^ 1];
+        case 2: return c->vel[c->front];
+        case 3: return c->acc;
+        default: return nullptr;
+    }
+}
+
+int gravb200_peak_probe(int device, double* out, int n) {
+    if (!out || n < 5) return fail(GRAVB200_EINVAL, "out needs room for 5 doubles");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(GRAVB200_ENODEV, "no CUDA device");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8;
+    void* buf = nullptr;
+    unsigned long long* clk = nullptr;
+    CU(cudaMalloc(&buf, (size_t)threads * blocks * sizeof(double)));
+    CU(cudaMalloc(&clk, 2 * sizeof(unsigned long long)));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    const double nthreads = (double)threads * blocks;
+    const double ops = nthreads * kProbeIters * kProbeChains;
+    float ms = 0;
+    auto best = [&](auto&& launch) -> double {
+        double bestms = 1e30;
+        for (int rep = 0; rep < 5; ++rep) {
+            cudaEventRecord(a);
+            launch();
+            cudaEventRecord(b);
+            cudaEventSynchronize(b);
+            cudaEventElapsedTime(&ms, a, b);
+            if (rep > 0 && ms < bestms) bestms = ms;
+        }
+        return bestms;
+    };
+    double t = best([&] { probe_ffma<<<blocks, threads>>>((float*)buf, 1.0001f, 0.5f, clk); });
+    out[0] = ops * 2 / (t * 1e-3) / 1e12;
+    unsigned long long hclk[2] = {0, 0};
+    CU(cudaMemcpy(hclk, clk, sizeof(hclk), cudaMemcpyDeviceToHost));
+    out[4] = hclk[1] ? (double)hclk[0] / (double)hclk[1] * 1e3 : 0.0;   // cycles per ns -> MHz
+    t = best([&] { probe_ffma2<<<blocks, threads>>>((float*)buf, 1.0001f, 0.5f); });
+    out[1] = ops * 4 / (t * 1e-3) / 1e12;
+    t = best([&] { probe_dfma<<<blocks, threads>>>((double*)buf, 1.0001, 0.5); });
+    out[2] = ops * 2 / (t * 1e-3) / 1e12;
+    t = best([&] { probe_mufu<<<blocks, threads>>>((float*)buf); });
+    out[3] = ops / (t * 1e-3) / 1e9;
+    CU(cudaGetLastError());
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(buf);
+    cudaFree(clk);
+    return 0;
+}
+
+}  // extern "C"

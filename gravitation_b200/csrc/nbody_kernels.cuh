@@ -1,0 +1,467 @@
+// gravitation_b200 — all-pairs gravity sweep + fused symplectic-Euler integrate for sm_100a.
+//
+// What this restates (reference = pleiszenburg/gravitation, paths relative to its repo root):
+//   * stage 1, per-body N x N form:  a_i = G * sum_{j != i} m_j (r_j - r_i) / |r_j - r_i|^3
+//     src/gravitation/kernel/pc2.py:59-91 (i == j skipped by index, G applied once at the end),
+//     physics spec src/gravitation/kernel/py1.py:57-69.  No softening in the reference; eps2 = 0
+//     reproduces it, eps2 > 0 is an extension.
+//   * stage 2, array form:           a *= T; v += a; r += v*T   (each op rounded separately)
+//     src/gravitation/kernel/np2.py:110-115, pc2.py:164-168.
+//
+// How it is built for B200 (nothing here is a translation of pc2/pc3):
+//   * state is device resident: pos = {x,y,z,m} (float4 / double4), vel, acc; pos/vel are
+//     double-buffered so the fused integrate never overwrites what other CTAs still read.
+//   * j-tiles are staged in shared memory by TMA 1-D bulk copies (cp.async.bulk + mbarrier
+//     complete_tx) through a STAGES-deep full/empty ring; the consumer warps never execute a
+//     CTA-wide barrier inside the sweep.
+//   * each thread owns R i-bodies in registers; fp32 arithmetic is issued as packed f32x2
+//     (FADD2/FMUL2/FFMA2) over PAIRS of i-bodies, the j-body operand is a scalar register that the
+//     packed instruction broadcasts, so one LDS.128 (uniform address) feeds R interactions.
+//   * accumulation is hierarchical: fp32 inside one j-tile, fp64 across tiles (SURVEY finding 3).
+//   * work decomposition is stream-K over the flat (i-block, j-tile) space: every CTA gets the
+//     same number of tiles (+-1) whatever N is; i-blocks split between CTAs are combined by the
+//     last-arriving contributor in a fixed order (deterministic), which then runs the fused
+//     integrate epilogue.  No second launch, no host round trip.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gravb200 {
+
+struct SweepParams {
+    const void* pos_front;    // [n_pad] {x,y,z,m} of ALL bodies (read)
+    void* pos_back;           // [n_pad] same layout; local rows written by the epilogue
+    const void* vel_front;    // [n_local_pad] {vx,vy,vz,0} local rows (read)
+    void* vel_back;           // [n_local_pad] (written)
+    void* acc;                // [n_local_pad] {ax,ay,az,0} (written)
+    double* partial;          // [2*grid][IBLK][4] fp64 partial sums of split i-blocks
+    unsigned int* counters;   // [n_iblocks] tiles-arrived counters (self-resetting)
+    long long n_total;        // number of j-bodies (all bodies)
+    long long row0;           // global index of local row 0
+    long long n_local;        // local rows (i-bodies)
+    int n_iblocks;            // ceil(n_local / IBLK)
+    int n_jtiles;             // ceil(n_total / TILE)
+    double G, T;              // gravitational constant, time step
+    float eps2_f;             // softening^2 (fp32 kernel)
+    double eps2_d;            // softening^2 (fp64 kernel)
+    int integrate;            // 1: epilogue also writes vel_back / pos_back
+};
+
+// ------------------------------------------------------------------------------------------------
+// mbarrier / TMA bulk-copy helpers (PTX ISA 8.x, sm_90+; SASS: SYNCS.* and UBLKCP)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy, completion signalled on `bar` as transaction bytes
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                             uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // one MUFU.RSQ, 2 ulp
+    return y;
+}
+__device__ __forceinline__ double ld_cg_f64(const double* p) {
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+// stream-K partition helpers: CTA c owns flat tiles [lo(c), lo(c+1))
+__device__ __forceinline__ long long sk_lo(long long total, long long c, long long S) {
+    return total * c / S;
+}
+// the CTA that owns flat tile t
+__device__ __forceinline__ long long sk_owner(long long total, long long t, long long S) {
+    return ((t + 1) * S - 1) / total;
+}
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> { using type = float4; };
+template <> struct Vec4<double> { using type = double4; };
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue shared by both precisions: a = G * sum ; v' = v + a*T ; r' = r + v'*T
+// Each op rounded separately in the state dtype (np2.py:110-115) -- intrinsics forbid contraction.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void finalize_body(const SweepParams& p, long long i_local, double sx,
+                                              double sy, double sz, float4 ri, float /*tag*/) {
+    float ax = (float)(sx * p.G), ay = (float)(sy * p.G), az = (float)(sz * p.G);
+    ((float4*)p.acc)[i_local] = make_float4(ax, ay, az, 0.f);
+    if (p.integrate) {
+        const float T = (float)p.T;
+        float4 v = ((const float4*)p.vel_front)[i_local];
+        v.x = __fadd_rn(v.x, __fmul_rn(ax, T));
+        v.y = __fadd_rn(v.y, __fmul_rn(ay, T));
+        v.z = __fadd_rn(v.z, __fmul_rn(az, T));
+        ri.x = __fadd_rn(ri.x, __fmul_rn(v.x, T));
+        ri.y = __fadd_rn(ri.y, __fmul_rn(v.y, T));
+        ri.z = __fadd_rn(ri.z, __fmul_rn(v.z, T));
+        ((float4*)p.vel_back)[i_local] = v;
+        ((float4*)p.pos_back)[p.row0 + i_local] = ri;
+    }
+}
+__device__ __forceinline__ void finalize_body(const SweepParams& p, long long i_local, double sx,
+                                              double sy, double sz, double4 ri, double /*tag*/) {
+    double ax = __dmul_rn(sx, p.G), ay = __dmul_rn(sy, p.G), az = __dmul_rn(sz, p.G);
+    ((double4*)p.acc)[i_local] = make_double4(ax, ay, az, 0.0);
+    if (p.integrate) {
+        const double T = p.T;
+        double4 v = ((const double4*)p.vel_front)[i_local];
+        v.x = __dadd_rn(v.x, __dmul_rn(ax, T));
+        v.y = __dadd_rn(v.y, __dmul_rn(ay, T));
+        v.z = __dadd_rn(v.z, __dmul_rn(az, T));
+        ri.x = __dadd_rn(ri.x, __dmul_rn(v.x, T));
+        ri.y = __dadd_rn(ri.y, __dmul_rn(v.y, T));
+        ri.z = __dadd_rn(ri.z, __dmul_rn(v.z, T));
+        ((double4*)p.vel_back)[i_local] = v;
+        ((double4*)p.pos_back)[p.row0 + i_local] = ri;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The sweep kernel.
+//   REAL    float | double
+//   THREADS threads per CTA;  R i-bodies per thread (even for float);  IBLK = THREADS*R rows per
+//   i-block;  TILE j-bodies per shared-memory stage;  STAGES ring depth;  MINB min CTAs per SM.
+//   PACK    fp32 only: 1 = packed f32x2 over i-body pairs, 0 = scalar FFMA (kept for the ncu A/B).
+// Shared memory (dynamic): STAGES*TILE*sizeof(vec4) tile ring, then 2*STAGES mbarriers.
+// ------------------------------------------------------------------------------------------------
+template <typename REAL, int THREADS, int R, int TILE, int STAGES, int MINB, int PACK>
+__global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams p) {
+    using V4 = typename Vec4<REAL>::type;
+    constexpr int IBLK = THREADS * R;
+    constexpr int NWARPS = THREADS / 32;
+    constexpr bool F32 = sizeof(REAL) == 4;
+    static_assert(!F32 || (R % 2 == 0), "fp32 path packs pairs of i-bodies");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    V4* tiles = reinterpret_cast<V4*>(smem_raw);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * TILE * sizeof(V4));
+    uint64_t* empty_bar = full_bar + STAGES;
+    __shared__ int s_last;
+
+    const int tid = threadIdx.x;
+    const long long S = gridDim.x;
+    const long long nj = p.n_jtiles;
+    const long long total = (long long)p.n_iblocks * nj;
+    const long long lo = sk_lo(total, blockIdx.x, S);
+    const long long hi = sk_lo(total, blockIdx.x + 1, S);
+    if (lo >= hi) return;   // CTA-uniform
+    const int ntiles = (int)(hi - lo);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], NWARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const V4* __restrict__ posf = reinterpret_cast<const V4*>(p.pos_front);
+
+    // producer: one thread issues the TMA bulk copy of flat tile k into ring slot k % STAGES
+    auto issue_tile = [&](int k) {
+        const long long g = lo + k;
+        const long long jt = g % nj;
+        const long long j0 = jt * TILE;
+        long long cnt = p.n_total - j0;
+        if (cnt > TILE) cnt = TILE;
+        const uint32_t bytes = (uint32_t)(cnt * sizeof(V4));
+        const int s = k % STAGES;
+        mbar_expect_tx(&full_bar[s], bytes);
+        tma_bulk_g2s(tiles + (size_t)s * TILE, posf + j0, bytes, &full_bar[s]);
+    };
+    if (tid == 0) {
+        const int pre = ntiles < (STAGES - 1) ? ntiles : (STAGES - 1);
+        for (int k = 0; k < pre; ++k) issue_tile(k);
+    }
+
+    // per-thread i-body state
+    REAL xi[R], yi[R], zi[R], mi[R];
+    double sx[R], sy[R], sz[R];
+    long long cur_ib = -1;
+    long long seg_first = 0;   // first flat tile of the current segment
+
+    // --- segment completion: combine split i-blocks, then run the fused epilogue ---------------
+    auto finish_segment = [&](long long ib, long long g_first, long long g_end) {
+        const long long t0 = ib * nj, t1 = t0 + nj;
+        bool do_final = true;
+        if (!(g_first == t0 && g_end == t1)) {
+            // split i-block: publish my partial, last arriver reduces all contributors in order
+            const long long slot = 2 * (long long)blockIdx.x + ((lo >= t0) ? 0 : 1);
+            double* mine = p.partial + slot * (long long)IBLK * 4;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                double4 v = make_double4(sx[r], sy[r], sz[r], 0.0);
+                reinterpret_cast<double4*>(mine)[r * THREADS + tid] = v;
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned int mytiles = (unsigned int)(g_end - g_first);
+                const unsigned int old = atomicAdd(&p.counters[ib], mytiles);
+                const int last = (old + mytiles == (unsigned int)nj);
+                if (last) p.counters[ib] = 0;   // self-reset for the next launch
+                s_last = last;
+            }
+            __syncthreads();
+            do_final = (s_last != 0);
+            if (do_final) {
+                __threadfence();
+                const long long c_first = sk_owner(total, t0, S), c_last = sk_owner(total, t1 - 1, S);
+#pragma unroll
+                for (int r = 0; r < R; ++r) { sx[r] = 0.0; sy[r] = 0.0; sz[r] = 0.0; }
+                for (long long c = c_first; c <= c_last; ++c) {
+                    const long long clo = sk_lo(total, c, S), chi = sk_lo(total, c + 1, S);
+                    if (clo >= chi) continue;
+                    const long long cs = 2 * c + ((clo >= t0) ? 0 : 1);
+                    const double* src = p.partial + cs * (long long)IBLK * 4;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const double* q = src + (size_t)(r * THREADS + tid) * 4;
+                        sx[r] += ld_cg_f64(q + 0);
+                        sy[r] += ld_cg_f64(q + 1);
+                        sz[r] += ld_cg_f64(q + 2);
+                    }
+                }
+            }
+            __syncthreads();   // s_last may be rewritten by the next segment
+        }
+        if (do_final) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const long long il = ib * IBLK + r * THREADS + tid;
+                if (il < p.n_local) {
+                    V4 ri;
+                    ri.x = xi[r]; ri.y = yi[r]; ri.z = zi[r]; ri.w = mi[r];
+                    finalize_body(p, il, sx[r], sy[r], sz[r], ri, REAL(0));
+                }
+            }
+        }
+    };
+
+    for (int k = 0; k < ntiles; ++k) {
+        const long long g = lo + k;
+        const long long ib = g / nj;
+        const long long jt = g - ib * nj;
+        if (ib != cur_ib) {
+            if (cur_ib >= 0) finish_segment(cur_ib, seg_first, g);
+            cur_ib = ib;
+            seg_first = g;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const long long il = ib * IBLK + r * THREADS + tid;
+                V4 b;
+                b.x = 0; b.y = 0; b.z = 0; b.w = 0;
+                if (il < p.n_local) b = posf[p.row0 + il];
+                xi[r] = b.x; yi[r] = b.y; zi[r] = b.z; mi[r] = b.w;
+                sx[r] = 0.0; sy[r] = 0.0; sz[r] = 0.0;
+            }
+        }
+        // producer step: refill the slot freed by tile k-1 with tile k+STAGES-1
+        if (tid == 0) {
+            const int kk = k + STAGES - 1;
+            if (kk < ntiles) {
+                if (kk >= STAGES) mbar_wait(&empty_bar[kk % STAGES], ((kk / STAGES) - 1) & 1);
+                issue_tile(kk);
+            }
+        }
+        const int s = k % STAGES;
+        mbar_wait(&full_bar[s], (k / STAGES) & 1);
+        const V4* __restrict__ tile = tiles + (size_t)s * TILE;
+
+        const long long j0 = jt * TILE;
+        long long cntl = p.n_total - j0;
+        const int jn = cntl > TILE ? TILE : (int)cntl;
+        const long long ib_g0 = p.row0 + ib * IBLK;   // global index of the i-block's first row
+        const bool special = (jn < TILE) || (j0 < ib_g0 + IBLK && j0 + TILE > ib_g0);
+
+        if constexpr (F32) {
+            if constexpr (PACK) {
+                constexpr int P = R / 2;
+                float2 ax[P], ay[P], az[P];
+#pragma unroll
+                for (int q = 0; q < P; ++q) ax[q] = ay[q] = az[q] = make_float2(0.f, 0.f);
+                const float e2 = p.eps2_f;
+                if (!special) {
+#pragma unroll 2
+                    for (int j = 0; j < TILE; ++j) {
+                        const float4 b = tile[j];
+#pragma unroll
+                        for (int q = 0; q < P; ++q) {
+                            const float2 dx = __fadd2_rn(make_float2(b.x, b.x), make_float2(-xi[2 * q], -xi[2 * q + 1]));
+                            const float2 dy = __fadd2_rn(make_float2(b.y, b.y), make_float2(-yi[2 * q], -yi[2 * q + 1]));
+                            const float2 dz = __fadd2_rn(make_float2(b.z, b.z), make_float2(-zi[2 * q], -zi[2 * q + 1]));
+                            float2 d2 = __ffma2_rn(dx, dx, make_float2(e2, e2));
+                            d2 = __ffma2_rn(dy, dy, d2);
+                            d2 = __ffma2_rn(dz, dz, d2);
+                            const float2 ri = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
+                            const float2 ri2 = __fmul2_rn(ri, ri);
+                            const float2 mr = __fmul2_rn(make_float2(b.w, b.w), ri);
+                            const float2 sc = __fmul2_rn(mr, ri2);
+                            ax[q] = __ffma2_rn(dx, sc, ax[q]);
+                            ay[q] = __ffma2_rn(dy, sc, ay[q]);
+                            az[q] = __ffma2_rn(dz, sc, az[q]);
+                        }
+                    }
+                } else {
+                    // diagonal and/or ragged tile: exclude the self pair by index, stop at n_total
+                    const long long ibase = ib_g0 + tid;
+                    for (int j = 0; j < jn; ++j) {
+                        const float4 b = tile[j];
+                        const long long dj = (j0 + j) - ibase;
+#pragma unroll
+                        for (int q = 0; q < P; ++q) {
+                            const float2 dx = make_float2(b.x - xi[2 * q], b.x - xi[2 * q + 1]);
+                            const float2 dy = make_float2(b.y - yi[2 * q], b.y - yi[2 * q + 1]);
+                            const float2 dz = make_float2(b.z - zi[2 * q], b.z - zi[2 * q + 1]);
+                            float2 d2;
+                            d2.x = fmaf(dz.x, dz.x, fmaf(dy.x, dy.x, fmaf(dx.x, dx.x, e2)));
+                            d2.y = fmaf(dz.y, dz.y, fmaf(dy.y, dy.y, fmaf(dx.y, dx.y, e2)));
+                            const float2 ri = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
+                            float2 sc = make_float2((b.w * ri.x) * (ri.x * ri.x), (b.w * ri.y) * (ri.y * ri.y));
+                            if (dj == (long long)(2 * q) * THREADS) sc.x = 0.f;
+                            if (dj == (long long)(2 * q + 1) * THREADS) sc.y = 0.f;
+                            // the self pair has dx = 0 exactly; sc = 0 keeps it out (no inf*0)
+                            ax[q].x = fmaf(dx.x, sc.x, ax[q].x); ax[q].y = fmaf(dx.y, sc.y, ax[q].y);
+                            ay[q].x = fmaf(dy.x, sc.x, ay[q].x); ay[q].y = fmaf(dy.y, sc.y, ay[q].y);
+                            az[q].x = fmaf(dz.x, sc.x, az[q].x); az[q].y = fmaf(dz.y, sc.y, az[q].y);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < P; ++q) {
+                    sx[2 * q] += (double)ax[q].x; sx[2 * q + 1] += (double)ax[q].y;
+                    sy[2 * q] += (double)ay[q].x; sy[2 * q + 1] += (double)ay[q].y;
+                    sz[2 * q] += (double)az[q].x; sz[2 * q + 1] += (double)az[q].y;
+                }
+            } else {
+                float ax[R], ay[R], az[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) ax[r] = ay[r] = az[r] = 0.f;
+                const float e2 = p.eps2_f;
+                if (!special) {
+#pragma unroll 2
+                    for (int j = 0; j < TILE; ++j) {
+                        const float4 b = tile[j];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const float dx = b.x - xi[r], dy = b.y - yi[r], dz = b.z - zi[r];
+                            const float d2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, e2)));
+                            const float ri = rsqrt_approx(d2);
+                            const float sc = (b.w * ri) * (ri * ri);
+                            ax[r] = fmaf(dx, sc, ax[r]);
+                            ay[r] = fmaf(dy, sc, ay[r]);
+                            az[r] = fmaf(dz, sc, az[r]);
+                        }
+                    }
+                } else {
+                    const long long ibase = ib_g0 + tid;
+                    for (int j = 0; j < jn; ++j) {
+                        const float4 b = tile[j];
+                        const long long dj = (j0 + j) - ibase;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const float dx = b.x - xi[r], dy = b.y - yi[r], dz = b.z - zi[r];
+                            const float d2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, e2)));
+                            const float ri = rsqrt_approx(d2);
+                            float sc = (b.w * ri) * (ri * ri);
+                            if (dj == (long long)r * THREADS) sc = 0.f;
+                            ax[r] = fmaf(dx, sc, ax[r]);
+                            ay[r] = fmaf(dy, sc, ay[r]);
+                            az[r] = fmaf(dz, sc, az[r]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    sx[r] += (double)ax[r]; sy[r] += (double)ay[r]; sz[r] += (double)az[r];
+                }
+            }
+        } else {
+            // fp64: accumulate straight into the fp64 sums
+            const double e2 = p.eps2_d;
+            if (!special) {
+#pragma unroll 2
+                for (int j = 0; j < TILE; ++j) {
+                    const double4 b = tile[j];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const double dx = b.x - xi[r], dy = b.y - yi[r], dz = b.z - zi[r];
+                        const double d2 = fma(dz, dz, fma(dy, dy, fma(dx, dx, e2)));
+                        const double ri = rsqrt(d2);
+                        const double sc = (b.w * ri) * (ri * ri);
+                        sx[r] = fma(dx, sc, sx[r]);
+                        sy[r] = fma(dy, sc, sy[r]);
+                        sz[r] = fma(dz, sc, sz[r]);
+                    }
+                }
+            } else {
+                const long long ibase = ib_g0 + tid;
+                for (int j = 0; j < jn; ++j) {
+                    const double4 b = tile[j];
+                    const long long dj = (j0 + j) - ibase;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const double dx = b.x - xi[r], dy = b.y - yi[r], dz = b.z - zi[r];
+                        const double d2 = fma(dz, dz, fma(dy, dy, fma(dx, dx, e2)));
+                        const double ri = rsqrt(d2);
+                        double sc = (b.w * ri) * (ri * ri);
+                        if (dj == (long long)r * THREADS) sc = 0.0;
+                        sx[r] = fma(dx, sc, sx[r]);
+                        sy[r] = fma(dy, sc, sy[r]);
+                        sz[r] = fma(dz, sc, sz[r]);
+                    }
+                }
+            }
+        }
+        // consumer release: this warp is done reading ring slot s
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);
+    }
+    finish_segment(cur_ib, seg_first, hi);
+}
+
+template <typename REAL, int THREADS, int R, int TILE, int STAGES>
+constexpr size_t sweep_smem_bytes() {
+    return (size_t)STAGES * TILE * sizeof(typename Vec4<REAL>::type) + 2 * STAGES * sizeof(uint64_t);
+}
+
+}  // namespace gravb200

@@ -1,0 +1,106 @@
+/* gravb200.h — C ABI of the B200-native gravitation kernel (libgravb200.so).
+ *
+ * This is the drop-in boundary for ONE path of pleiszenburg/gravitation: the per-step hot loop
+ *     universe_base.step() -> step_stage1() [O(N^2)] -> step_stage2() [O(N)]
+ *     (reference: src/gravitation/kernel/_base_.py:136-161).
+ * A kernel module `src/gravitation/kernel/b200.py` binds these entry points with ctypes exactly the
+ * way the reference's own native kernels bind theirs (c1a.py:72-83 / c4b.py:86-93 bind
+ * `step_stage1(struct univ*)` from _lib1_/lib.c:52 and _lib4_/lib.c:376).  See INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 on success and a negative
+ * GRAVB200_E* code on failure, with a human readable message in gravb200_last_error().  The library
+ * never falls back to the CPU: without a usable CUDA device every compute entry point fails.
+ *
+ * One context = one shard = one GPU.  Multi-GPU runs use one context per GPU (one process per GPU
+ * under torchrun, or several contexts in one process); rows are partitioned contiguously and
+ * positions are exchanged once per step.
+ */
+#ifndef GRAVB200_H
+#define GRAVB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRAVB200_F32 0 /* reference dtype='float32' (default, _base_.py:75) */
+#define GRAVB200_F64 1 /* reference dtype='float64' */
+
+#define GRAVB200_OK 0
+#define GRAVB200_EINVAL (-1)  /* bad argument / wrong call order */
+#define GRAVB200_ECUDA (-2)   /* CUDA runtime failure (message has the CUDA error string) */
+#define GRAVB200_ENCCL (-3)   /* NCCL failure or NCCL not loadable */
+#define GRAVB200_ENODEV (-4)  /* no CUDA device */
+
+#define GRAVB200_NCCL_ID_BYTES 128
+
+typedef struct gravb200_ctx gravb200_ctx;
+
+/* Library / device probes (no compute). */
+int gravb200_abi_version(void);
+int gravb200_device_count(void);
+const char* gravb200_last_error(void);
+
+/* Replaces: pc2.py:96-145 `start_kernel` (allocation of device arrays, launch geometry).
+ * n_total: number of bodies; dtype: GRAVB200_F32/F64; device: CUDA ordinal;
+ * rank/world: this shard's index and the number of shards (world == 1: single GPU);
+ * nccl_id: GRAVB200_NCCL_ID_BYTES bytes from gravb200_nccl_unique_id() on rank 0 (NULL iff world == 1). */
+int gravb200_ctx_create(int64_t n_total, int dtype, int device, int rank, int world,
+                        const void* nccl_id, gravb200_ctx** out);
+int gravb200_ctx_destroy(gravb200_ctx* ctx); /* replaces stop_kernel(), _base_.py:174-177 */
+
+/* rank 0 fills `id` (GRAVB200_NCCL_ID_BYTES); the caller distributes it to the other ranks. */
+int gravb200_nccl_unique_id(void* id);
+
+/* Replaces: the per-step 3x memcpy_htod of pc2.py:149-151 plus the mass upload of pc2.py:131.
+ * r, v: [n_total][3] C-contiguous, m: [n_total], in the context dtype. Caller-owned, copied, never
+ * retained. G, T as universe_base holds them (_base_.py:83-88); eps = softening length (reference: 0). */
+int gravb200_upload(gravb200_ctx* ctx, const void* r, const void* v, const void* m, double G,
+                    double T, double eps);
+/* Positions only (a caller that moved bodies on the host between steps, e.g. pc2's host-side stage 2). */
+int gravb200_upload_positions(gravb200_ctx* ctx, const void* r);
+
+/* Replaces: step_stage1() (pc2.py:147-162 kernel launch).  Asynchronous.  Computes accelerations of
+ * this shard's rows AND, in the same kernel's epilogue, v' and r' into back buffers; front state is
+ * untouched, so accelerations can be read between stage1 and stage2 as with every reference kernel. */
+int gravb200_stage1(gravb200_ctx* ctx);
+/* Replaces: step_stage2() (np2.py:110-115 / pc2.py:164-168).  Commits the back buffers (multi-GPU:
+ * after the all-gather of new positions) and blocks until the device is idle. */
+int gravb200_stage2(gravb200_ctx* ctx);
+/* k fused steps without host involvement (launch-bound small N: captured in a CUDA graph). */
+int gravb200_steps(gravb200_ctx* ctx, int k);
+int gravb200_sync(gravb200_ctx* ctx);
+
+/* Replaces: the 3x memcpy_dtoh of pc2.py:160-162 and the row views of np2.py:70-75.
+ * r: [n_total][3] (all bodies); v, a: [n_local][3] rows [row0, row0+n_local) of this shard
+ * (world == 1: all bodies).  Any pointer may be NULL. */
+int gravb200_download(gravb200_ctx* ctx, void* r, void* v, void* a);
+int gravb200_shard(const gravb200_ctx* ctx, int64_t* row0, int64_t* n_local);
+
+/* Device-side timings (cudaEvent): ms[0] = last stage1 sweep kernel, ms[1] = last exchange,
+ * ms[2] = total of the last gravb200_steps() call; n = capacity of ms. */
+int gravb200_timings(gravb200_ctx* ctx, float* ms, int n);
+
+/* Introspection used by bench.py / tests: launch geometry and counters.
+ * info[0]=grid, [1]=threads, [2]=i-bodies per thread, [3]=j tile, [4]=stages, [5]=dynamic smem bytes,
+ * [6]=kernel launches so far, [7]=SM count, [8]=packed f32x2 (1/0), [9]=resident CTAs per SM. */
+int gravb200_info(const gravb200_ctx* ctx, int64_t* info, int n);
+/* Force a kernel variant (tests / ncu A-B): variant < 0 restores the automatic choice. */
+int gravb200_set_variant(gravb200_ctx* ctx, int variant);
+int gravb200_variant_count(int dtype);
+const char* gravb200_variant_name(int dtype, int variant);
+
+/* Raw device pointers of the shard state (for peer access / torch interop in tests).
+ * which: 0 = pos front, 1 = pos back, 2 = vel front, 3 = acc. */
+void* gravb200_device_ptr(gravb200_ctx* ctx, int which);
+
+/* FP32/FP64 FMA-chain microbenchmark on `device` (measured non-tensor peak).
+ * out[0] = fp32 FFMA TFLOP/s, out[1] = packed FFMA2 TFLOP/s, out[2] = fp64 DFMA TFLOP/s,
+ * out[3] = MUFU.RSQ G op/s, out[4] = SM clock MHz observed during the fp32 run. */
+int gravb200_peak_probe(int device, double* out, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAVB200_H */
