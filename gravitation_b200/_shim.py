@@ -39,6 +39,9 @@ _SIGNATURES = [
 	('gravb200_upload_positions', ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
 	('gravb200_stage1', ctypes.c_int, [_c_ctx]),
 	('gravb200_stage2', ctypes.c_int, [_c_ctx]),
+	('gravb200_exchange', ctypes.c_int, [_c_ctx]),
+	('gravb200_group_begin', ctypes.c_int, []),
+	('gravb200_group_end', ctypes.c_int, []),
 	('gravb200_steps', ctypes.c_int, [_c_ctx, ctypes.c_int]),
 	('gravb200_sync', ctypes.c_int, [_c_ctx]),
 	('gravb200_download', ctypes.c_int, [_c_ctx, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -92,6 +95,14 @@ def nccl_unique_id():
 	buf = ctypes.create_string_buffer(NCCL_ID_BYTES)
 	_check(load().gravb200_nccl_unique_id(buf))
 	return buf.raw
+
+
+def group_begin():
+	_check(load().gravb200_group_begin())
+
+
+def group_end():
+	_check(load().gravb200_group_end())
 
 
 def peak_probe(device = 0):
@@ -158,6 +169,9 @@ class Shard:
 	def stage1(self):
 		_check(self._lib.gravb200_stage1(self._ctx))
 
+	def exchange(self):
+		_check(self._lib.gravb200_exchange(self._ctx))
+
 	def stage2(self):
 		_check(self._lib.gravb200_stage2(self._ctx))
 
@@ -175,15 +189,18 @@ class Shard:
 			out_v = np.empty((self.n_local, 3), dtype = self._np)
 		if a and out_a is None:
 			out_a = np.empty((self.n_local, 3), dtype = self._np)
+		for arr in (out_r, out_v, out_a):
+			if arr is not None and not (arr.flags.c_contiguous and arr.dtype == self._np):
+				raise ValueError('download targets must be C-contiguous arrays of dtype %s' % self.dtype)
 		_check(self._lib.gravb200_download(
 			self._ctx, _ptr(out_r if r else None), _ptr(out_v if v else None), _ptr(out_a if a else None),
 			))
 		return (out_r if r else None, out_v if v else None, out_a if a else None)
 
 	def timings(self):
-		ms = (ctypes.c_float * 3)()
-		_check(self._lib.gravb200_timings(self._ctx, ms, 3))
-		return dict(sweep_ms = ms[0], exchange_ms = ms[1], steps_ms = ms[2])
+		ms = (ctypes.c_float * 4)()
+		_check(self._lib.gravb200_timings(self._ctx, ms, 4))
+		return dict(sweep_ms = ms[0], exchange_ms = ms[1], steps_ms = ms[2], sm_mhz = ms[3])
 
 	def info(self):
 		v = (ctypes.c_int64 * 10)()

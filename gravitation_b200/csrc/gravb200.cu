@@ -55,6 +55,8 @@ struct NcclApi {
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     bool tried = false;
 };
 NcclApi g_nccl;
@@ -78,6 +80,8 @@ int nccl_load() {
     SYM(AllGather, "ncclAllGather");
     SYM(CommDestroy, "ncclCommDestroy");
     SYM(GetErrorString, "ncclGetErrorString");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
 #undef SYM
     return 0;
 }
@@ -98,40 +102,44 @@ struct Variant {
     const void* fn;
 };
 
-template <typename REAL, int THREADS, int R, int TILE, int STAGES, int MINB, int PACK>
+template <typename REAL, int THREADS, int R, int TILE, int STAGES, int MINB, int PACK, int UNROLL, int PREF>
 Variant make_variant(const char* name) {
     Variant v;
     v.name = name;
     v.threads = THREADS; v.r = R; v.tile = TILE; v.stages = STAGES; v.minb = MINB; v.pack = PACK;
     v.smem = sweep_smem_bytes<REAL, THREADS, R, TILE, STAGES>();
-    v.fn = (const void*)&sweep_kernel<REAL, THREADS, R, TILE, STAGES, MINB, PACK>;
+    v.fn = (const void*)&sweep_kernel<REAL, THREADS, R, TILE, STAGES, MINB, PACK, UNROLL, PREF>;
     return v;
 }
 
 // Ordered large -> small work granularity; the automatic choice takes the first one that still
 // gives every resident CTA >= 8 tiles (see pick_variant).  Entries after the "auto" prefix are
 // only reachable through gravb200_set_variant (ncu A/B evidence, tuning sweeps).
-#define V32(T, R, TILE, ST, MB, PK) \
-    make_variant<float, T, R, TILE, ST, MB, PK>("f32_t" #T "_r" #R "_j" #TILE "_s" #ST "_b" #MB "_p" #PK)
-#define V64(T, R, TILE, ST, MB) \
-    make_variant<double, T, R, TILE, ST, MB, 0>("f64_t" #T "_r" #R "_j" #TILE "_s" #ST "_b" #MB)
+#define V32(T, R, TILE, ST, MB, PK, U, PF) \
+    make_variant<float, T, R, TILE, ST, MB, PK, U, PF>("f32_t" #T "_r" #R "_j" #TILE "_s" #ST "_b" #MB "_p" #PK "_u" #U "_f" #PF)
+#define V64(T, R, TILE, ST, MB, U) \
+    make_variant<double, T, R, TILE, ST, MB, 0, U, 0>("f64_t" #T "_r" #R "_j" #TILE "_s" #ST "_b" #MB "_u" #U)
 
 const std::vector<Variant>& variants_f32() {
     static const std::vector<Variant> v = {
-        V32(256, 8, 512, 3, 2, 1),   // 0  auto: large N
-        V32(256, 4, 256, 3, 2, 1),   // 1  auto
-        V32(128, 4, 128, 3, 4, 1),   // 2  auto
-        V32(128, 2, 64, 4, 4, 1),    // 3  auto: tiny N
-        V32(256, 8, 512, 3, 2, 0),   // 4  scalar-FFMA twin of 0 (A/B)
-        V32(256, 4, 256, 3, 2, 0),   // 5  scalar-FFMA twin of 1
-        V32(128, 8, 512, 3, 4, 1),   // 6
-        V32(256, 8, 256, 4, 2, 1),   // 7
-        V32(256, 8, 1024, 2, 2, 1),  // 8
-        V32(512, 4, 512, 3, 1, 1),   // 9
-        V32(256, 6, 512, 3, 2, 1),   // 10
-        V32(256, 12, 512, 3, 1, 1),  // 11
-        V32(128, 8, 512, 3, 2, 1),   // 12
-        V32(256, 8, 512, 3, 1, 1),   // 13
+        V32(256, 8, 512, 3, 1, 1, 2, 0),    // 0  auto: large N   (IBLK 2048)
+        V32(256, 4, 256, 3, 2, 1, 2, 0),    // 1  auto            (IBLK 1024)
+        V32(128, 4, 128, 3, 4, 1, 2, 0),    // 2  auto            (IBLK 512)
+        V32(128, 2, 64, 4, 4, 1, 2, 0),     // 3  auto: tiny N    (IBLK 256)
+        V32(256, 8, 512, 3, 1, 0, 2, 0),    // 4  scalar-FFMA twin of 0 (A/B evidence)
+        V32(512, 4, 512, 3, 1, 1, 2, 0),    // 5
+        V32(256, 8, 512, 3, 1, 1, 2, 1),    // 6  0 + prefetch
+        V32(512, 4, 512, 3, 1, 1, 2, 1),    // 7  5 + prefetch
+        V32(384, 8, 512, 3, 1, 1, 2, 0),    // 8
+        V32(384, 8, 512, 3, 1, 1, 2, 1),    // 9
+        V32(320, 8, 512, 3, 1, 1, 2, 0),    // 10
+        V32(320, 8, 512, 3, 1, 1, 2, 1),    // 11
+        V32(256, 8, 512, 3, 1, 1, 1, 1),    // 12
+        V32(256, 8, 512, 3, 1, 1, 4, 1),    // 13
+        V32(512, 4, 512, 3, 1, 1, 4, 1),    // 14
+        V32(384, 6, 512, 3, 1, 1, 2, 1),    // 15
+        V32(256, 10, 512, 3, 1, 1, 2, 0),   // 16
+        V32(256, 10, 512, 3, 1, 1, 2, 1),   // 17
     };
     return v;
 }
@@ -139,12 +147,14 @@ constexpr int kAutoF32 = 4;
 
 const std::vector<Variant>& variants_f64() {
     static const std::vector<Variant> v = {
-        V64(256, 4, 256, 3, 2),   // 0 auto: large N
-        V64(128, 2, 128, 3, 4),   // 1 auto
-        V64(128, 1, 64, 4, 4),    // 2 auto: tiny N
-        V64(256, 2, 256, 3, 2),   // 3
-        V64(128, 4, 256, 3, 4),   // 4
-        V64(256, 6, 256, 3, 1),   // 5
+        V64(256, 2, 256, 3, 2, 2),   // 0 auto: large N
+        V64(128, 2, 128, 3, 4, 2),   // 1 auto
+        V64(128, 1, 64, 4, 4, 2),    // 2 auto: tiny N
+        V64(256, 4, 256, 3, 2, 2),   // 3
+        V64(512, 2, 256, 3, 1, 2),   // 4
+        V64(256, 2, 256, 3, 2, 4),   // 5
+        V64(256, 2, 256, 3, 2, 1),   // 6
+        V64(512, 1, 256, 3, 2, 2),   // 7
     };
     return v;
 }
@@ -187,6 +197,7 @@ struct gravb200_ctx {
     int64_t n_total = 0, chunk = 0, n_pad = 0, row0 = 0, n_local = 0;
     double G = 0, T = 0, eps = 0;
     bool uploaded = false, pending = false;   // pending: stage1 issued, stage2 not yet
+    bool exchanged = false;                   // the position exchange of the pending step is enqueued
     int front = 0;
     void* pos[2] = {nullptr, nullptr};
     void* vel[2] = {nullptr, nullptr};
@@ -197,6 +208,7 @@ struct gravb200_ctx {
     size_t counters_n = 0;
     void* stage3 = nullptr;     // device staging for (N,3) host arrays
     void* stagem = nullptr;
+    unsigned long long* clk = nullptr;   // {SM cycles, ns} of CTA 0 of the last sweep
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_sweep = false, ev_xchg = false, ev_steps = false;
@@ -293,6 +305,7 @@ int launch_sweep(gravb200_ctx* c, int integrate) {
     p.eps2_f = (float)(c->eps * c->eps);
     p.eps2_d = c->eps * c->eps;
     p.integrate = integrate;
+    p.clk = c->clk;
     void* args[] = {&p};
     CU(cudaLaunchKernel(v.fn, dim3(c->grid), dim3(v.threads), args, v.smem, c->stream));
     c->launches++;
@@ -523,6 +536,8 @@ int gravb200_ctx_create(int64_t n_total, int dtype, int device, int rank, int wo
     CUX(cudaMemsetAsync(c->acc, 0, (size_t)c->chunk * v4, c->stream));
     CUX(cudaMalloc(&c->stage3, (size_t)n_total * 3 * c->esz));
     CUX(cudaMalloc(&c->stagem, (size_t)n_total * c->esz));
+    CUX(cudaMalloc(&c->clk, 2 * sizeof(unsigned long long)));
+    CUX(cudaMemsetAsync(c->clk, 0, 2 * sizeof(unsigned long long), c->stream));
 #undef CUX
     if (world > 1) {
         int rc = nccl_load();
@@ -555,6 +570,7 @@ int gravb200_ctx_destroy(gravb200_ctx* c) {
     if (c->counters) cudaFree(c->counters);
     if (c->stage3) cudaFree(c->stage3);
     if (c->stagem) cudaFree(c->stagem);
+    if (c->clk) cudaFree(c->clk);
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -601,20 +617,43 @@ int gravb200_stage1(gravb200_ctx* c) {
     CU(cudaEventRecord(c->ev[1], c->stream));
     c->ev_sweep = true;
     c->pending = true;
+    c->exchanged = false;
+    return 0;
+}
+
+int gravb200_exchange(gravb200_ctx* c) {
+    if (!c) return fail(GRAVB200_EINVAL, "ctx is NULL");
+    if (!c->pending) return fail(GRAVB200_EINVAL, "exchange without a preceding stage1");
+    if (c->exchanged || c->world == 1) return 0;
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->ev[2], c->stream));
+    int rc = exchange(c);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev[3], c->stream));
+    c->ev_xchg = true;
+    c->exchanged = true;
+    return 0;
+}
+
+int gravb200_group_begin(void) {
+    int rc = nccl_load();
+    if (rc) return rc;
+    NC(g_nccl.GroupStart());
+    return 0;
+}
+int gravb200_group_end(void) {
+    int rc = nccl_load();
+    if (rc) return rc;
+    NC(g_nccl.GroupEnd());
     return 0;
 }
 
 int gravb200_stage2(gravb200_ctx* c) {
     if (!c) return fail(GRAVB200_EINVAL, "ctx is NULL");
     if (!c->pending) return fail(GRAVB200_EINVAL, "stage2 without a preceding stage1");
+    int rc = gravb200_exchange(c);
+    if (rc) return rc;
     CU(cudaSetDevice(c->device));
-    if (c->world > 1) {
-        CU(cudaEventRecord(c->ev[2], c->stream));
-        int rc = exchange(c);
-        if (rc) return rc;
-        CU(cudaEventRecord(c->ev[3], c->stream));
-        c->ev_xchg = true;
-    }
     CU(cudaStreamSynchronize(c->stream));
     c->front ^= 1;
     c->pending = false;
@@ -670,6 +709,11 @@ int gravb200_timings(gravb200_ctx* c, float* ms, int n) {
     if (n > 0 && c->ev_sweep) CU(cudaEventElapsedTime(&ms[0], c->ev[0], c->ev[1]));
     if (n > 1 && c->ev_xchg) CU(cudaEventElapsedTime(&ms[1], c->ev[2], c->ev[3]));
     if (n > 2 && c->ev_steps) CU(cudaEventElapsedTime(&ms[2], c->ev[0], c->ev[1]));
+    if (n > 3) {
+        unsigned long long h[2] = {0, 0};
+        CU(cudaMemcpy(h, c->clk, sizeof(h), cudaMemcpyDeviceToHost));
+        ms[3] = h[1] ? (float)((double)h[0] / (double)h[1] * 1e3) : -1.f;   // cycles/ns -> MHz
+    }
     return 0;
 }
 

@@ -46,6 +46,7 @@ struct SweepParams {
     float eps2_f;             // softening^2 (fp32 kernel)
     double eps2_d;            // softening^2 (fp64 kernel)
     int integrate;            // 1: epilogue also writes vel_back / pos_back
+    unsigned long long* clk;  // optional [2]: CTA 0 writes {SM cycles, ns} of its lifetime (clock evidence)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -160,9 +161,11 @@ __device__ __forceinline__ void finalize_body(const SweepParams& p, long long i_
 //   THREADS threads per CTA;  R i-bodies per thread (even for float);  IBLK = THREADS*R rows per
 //   i-block;  TILE j-bodies per shared-memory stage;  STAGES ring depth;  MINB min CTAs per SM.
 //   PACK    fp32 only: 1 = packed f32x2 over i-body pairs, 0 = scalar FFMA (kept for the ncu A/B).
+//   UNROLL  j-bodies per trip of the inner loop.
+//   PREF    fp32 packed path: 1 = explicit register prefetch of the next trip's j-bodies.
 // Shared memory (dynamic): STAGES*TILE*sizeof(vec4) tile ring, then 2*STAGES mbarriers.
 // ------------------------------------------------------------------------------------------------
-template <typename REAL, int THREADS, int R, int TILE, int STAGES, int MINB, int PACK>
+template <typename REAL, int THREADS, int R, int TILE, int STAGES, int MINB, int PACK, int UNROLL, int PREF>
 __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams p) {
     using V4 = typename Vec4<REAL>::type;
     constexpr int IBLK = THREADS * R;
@@ -196,36 +199,54 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
 
     const V4* __restrict__ posf = reinterpret_cast<const V4*>(p.pos_front);
 
-    // producer: one thread issues the TMA bulk copy of flat tile k into ring slot k % STAGES
-    auto issue_tile = [&](int k) {
-        const long long g = lo + k;
-        const long long jt = g % nj;
-        const long long j0 = jt * TILE;
+    unsigned long long clk0 = 0, ns0 = 0;
+    if (p.clk && blockIdx.x == 0 && tid == 0) {
+        clk0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+    }
+
+    // flat tile lo = (i-block ib0, j-tile jt0); both indices are advanced incrementally from here
+    // on (no 64-bit division on the per-tile path)
+    const int ib0 = (int)(lo / nj);
+    const int jt0 = (int)(lo - (long long)ib0 * nj);
+    const int njt = p.n_jtiles;
+
+    // producer: one thread issues the TMA bulk copies in flat-tile order into ring slot k % STAGES
+    int p_jt = jt0, p_slot = 0;   // only meaningful in thread 0
+    auto issue_next = [&]() {
+        const long long j0 = (long long)p_jt * TILE;
         long long cnt = p.n_total - j0;
         if (cnt > TILE) cnt = TILE;
         const uint32_t bytes = (uint32_t)(cnt * sizeof(V4));
-        const int s = k % STAGES;
-        mbar_expect_tx(&full_bar[s], bytes);
-        tma_bulk_g2s(tiles + (size_t)s * TILE, posf + j0, bytes, &full_bar[s]);
+        mbar_expect_tx(&full_bar[p_slot], bytes);
+        tma_bulk_g2s(tiles + (size_t)p_slot * TILE, posf + j0, bytes, &full_bar[p_slot]);
+        if (++p_jt == njt) p_jt = 0;
+        if (++p_slot == STAGES) p_slot = 0;
     };
     if (tid == 0) {
         const int pre = ntiles < (STAGES - 1) ? ntiles : (STAGES - 1);
-        for (int k = 0; k < pre; ++k) issue_tile(k);
+        for (int k = 0; k < pre; ++k) issue_next();
     }
 
     // per-thread i-body state
     REAL xi[R], yi[R], zi[R], mi[R];
     double sx[R], sy[R], sz[R];
-    long long cur_ib = -1;
-    long long seg_first = 0;   // first flat tile of the current segment
+    int ib = ib0, jt = jt0;    // current flat tile
+    int seg_tiles = 0;         // tiles accumulated into the current segment
+    int seg_index = 0;         // 0 for this CTA's first segment
+    bool new_block = true;
+    int c_slot = 0;            // consumer ring slot
+    uint32_t c_parity = 0;     // parity of the full barrier for the current ring lap
+    uint32_t e_parity = 0;     // (thread 0) parity of the empty barrier the producer waits on next
+    int e_slot = 0;
 
     // --- segment completion: combine split i-blocks, then run the fused epilogue ---------------
-    auto finish_segment = [&](long long ib, long long g_first, long long g_end) {
-        const long long t0 = ib * nj, t1 = t0 + nj;
+    auto finish_segment = [&]() {
+        const long long t0 = (long long)ib * nj, t1 = t0 + nj;
         bool do_final = true;
-        if (!(g_first == t0 && g_end == t1)) {
+        if (seg_tiles != njt) {
             // split i-block: publish my partial, last arriver reduces all contributors in order
-            const long long slot = 2 * (long long)blockIdx.x + ((lo >= t0) ? 0 : 1);
+            const long long slot = 2 * (long long)blockIdx.x + (seg_index == 0 ? 0 : 1);
             double* mine = p.partial + slot * (long long)IBLK * 4;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -235,7 +256,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
             __threadfence();
             __syncthreads();
             if (tid == 0) {
-                const unsigned int mytiles = (unsigned int)(g_end - g_first);
+                const unsigned int mytiles = (unsigned int)seg_tiles;
                 const unsigned int old = atomicAdd(&p.counters[ib], mytiles);
                 const int last = (old + mytiles == (unsigned int)nj);
                 if (last) p.counters[ib] = 0;   // self-reset for the next launch
@@ -267,7 +288,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
         if (do_final) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const long long il = ib * IBLK + r * THREADS + tid;
+                const long long il = (long long)ib * IBLK + r * THREADS + tid;
                 if (il < p.n_local) {
                     V4 ri;
                     ri.x = xi[r]; ri.y = yi[r]; ri.z = zi[r]; ri.w = mi[r];
@@ -278,16 +299,11 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
     };
 
     for (int k = 0; k < ntiles; ++k) {
-        const long long g = lo + k;
-        const long long ib = g / nj;
-        const long long jt = g - ib * nj;
-        if (ib != cur_ib) {
-            if (cur_ib >= 0) finish_segment(cur_ib, seg_first, g);
-            cur_ib = ib;
-            seg_first = g;
+        if (new_block) {
+            new_block = false;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const long long il = ib * IBLK + r * THREADS + tid;
+                const long long il = (long long)ib * IBLK + r * THREADS + tid;
                 V4 b;
                 b.x = 0; b.y = 0; b.z = 0; b.w = 0;
                 if (il < p.n_local) b = posf[p.row0 + il];
@@ -299,18 +315,22 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
         if (tid == 0) {
             const int kk = k + STAGES - 1;
             if (kk < ntiles) {
-                if (kk >= STAGES) mbar_wait(&empty_bar[kk % STAGES], ((kk / STAGES) - 1) & 1);
-                issue_tile(kk);
+                if (kk >= STAGES) {
+                    mbar_wait(&empty_bar[e_slot], e_parity);
+                    if (++e_slot == STAGES) { e_slot = 0; e_parity ^= 1; }
+                }
+                issue_next();
             }
         }
-        const int s = k % STAGES;
-        mbar_wait(&full_bar[s], (k / STAGES) & 1);
+        const int s = c_slot;
+        mbar_wait(&full_bar[s], c_parity);
+        if (++c_slot == STAGES) { c_slot = 0; c_parity ^= 1; }
         const V4* __restrict__ tile = tiles + (size_t)s * TILE;
 
-        const long long j0 = jt * TILE;
+        const long long j0 = (long long)jt * TILE;
         long long cntl = p.n_total - j0;
         const int jn = cntl > TILE ? TILE : (int)cntl;
-        const long long ib_g0 = p.row0 + ib * IBLK;   // global index of the i-block's first row
+        const long long ib_g0 = p.row0 + (long long)ib * IBLK;   // global index of the i-block's first row
         const bool special = (jn < TILE) || (j0 < ib_g0 + IBLK && j0 + TILE > ib_g0);
 
         if constexpr (F32) {
@@ -321,9 +341,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
                 for (int q = 0; q < P; ++q) ax[q] = ay[q] = az[q] = make_float2(0.f, 0.f);
                 const float e2 = p.eps2_f;
                 if (!special) {
-#pragma unroll 2
-                    for (int j = 0; j < TILE; ++j) {
-                        const float4 b = tile[j];
+                    auto interact = [&](const float4 b) {
 #pragma unroll
                         for (int q = 0; q < P; ++q) {
                             const float2 dx = __fadd2_rn(make_float2(b.x, b.x), make_float2(-xi[2 * q], -xi[2 * q + 1]));
@@ -340,6 +358,26 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
                             ay[q] = __ffma2_rn(dy, sc, ay[q]);
                             az[q] = __ffma2_rn(dz, sc, az[q]);
                         }
+                    };
+                    if constexpr (PREF) {
+                        // software-pipelined: the LDS.128s of trip t+1 are issued before the math of trip t
+                        float4 nxt[UNROLL];
+#pragma unroll
+                        for (int u = 0; u < UNROLL; ++u) nxt[u] = tile[u];
+#pragma unroll 1
+                        for (int j = 0; j < TILE; j += UNROLL) {
+                            float4 cur[UNROLL];
+#pragma unroll
+                            for (int u = 0; u < UNROLL; ++u) cur[u] = nxt[u];
+                            const int jn2 = (j + UNROLL < TILE) ? (j + UNROLL) : 0;
+#pragma unroll
+                            for (int u = 0; u < UNROLL; ++u) nxt[u] = tile[jn2 + u];
+#pragma unroll
+                            for (int u = 0; u < UNROLL; ++u) interact(cur[u]);
+                        }
+                    } else {
+#pragma unroll UNROLL
+                        for (int j = 0; j < TILE; ++j) interact(tile[j]);
                     }
                 } else {
                     // diagonal and/or ragged tile: exclude the self pair by index, stop at n_total
@@ -378,7 +416,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
                 for (int r = 0; r < R; ++r) ax[r] = ay[r] = az[r] = 0.f;
                 const float e2 = p.eps2_f;
                 if (!special) {
-#pragma unroll 2
+#pragma unroll UNROLL
                     for (int j = 0; j < TILE; ++j) {
                         const float4 b = tile[j];
 #pragma unroll
@@ -419,7 +457,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
             // fp64: accumulate straight into the fp64 sums
             const double e2 = p.eps2_d;
             if (!special) {
-#pragma unroll 2
+#pragma unroll UNROLL
                 for (int j = 0; j < TILE; ++j) {
                     const double4 b = tile[j];
 #pragma unroll
@@ -455,8 +493,21 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
         // consumer release: this warp is done reading ring slot s
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);
+
+        ++seg_tiles;
+        if (++jt == njt || k == ntiles - 1) {
+            finish_segment();
+            jt = 0; ++ib;
+            seg_tiles = 0; ++seg_index;
+            new_block = true;
+        }
     }
-    finish_segment(cur_ib, seg_first, hi);
+    if (p.clk && blockIdx.x == 0 && tid == 0) {
+        unsigned long long ns1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+        p.clk[0] = clock64() - clk0;
+        p.clk[1] = ns1 - ns0;
+    }
 }
 
 template <typename REAL, int THREADS, int R, int TILE, int STAGES>

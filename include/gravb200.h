@@ -68,6 +68,12 @@ int gravb200_stage1(gravb200_ctx* ctx);
 /* Replaces: step_stage2() (np2.py:110-115 / pc2.py:164-168).  Commits the back buffers (multi-GPU:
  * after the all-gather of new positions) and blocks until the device is idle. */
 int gravb200_stage2(gravb200_ctx* ctx);
+/* Multi-GPU only: enqueue the all-gather of the new positions of the pending step without waiting
+ * (gravb200_stage2 does it itself if it was not called).  A host thread that drives SEVERAL contexts must
+ * bracket their gravb200_exchange calls with gravb200_group_begin/end (ncclGroupStart/End semantics). */
+int gravb200_exchange(gravb200_ctx* ctx);
+int gravb200_group_begin(void);
+int gravb200_group_end(void);
 /* k fused steps without host involvement (launch-bound small N: captured in a CUDA graph). */
 int gravb200_steps(gravb200_ctx* ctx, int k);
 int gravb200_sync(gravb200_ctx* ctx);
@@ -79,7 +85,8 @@ int gravb200_download(gravb200_ctx* ctx, void* r, void* v, void* a);
 int gravb200_shard(const gravb200_ctx* ctx, int64_t* row0, int64_t* n_local);
 
 /* Device-side timings (cudaEvent): ms[0] = last stage1 sweep kernel, ms[1] = last exchange,
- * ms[2] = total of the last gravb200_steps() call; n = capacity of ms. */
+ * ms[2] = total of the last gravb200_steps() call, ms[3] = SM clock (MHz) that CTA 0 of the last sweep
+ * observed over its lifetime (clock64 / globaltimer); n = capacity of ms. */
 int gravb200_timings(gravb200_ctx* ctx, float* ms, int n);
 
 /* Introspection used by bench.py / tests: launch geometry and counters.

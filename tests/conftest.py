@@ -1,0 +1,42 @@
+# -*- coding: utf-8 -*-
+"""pytest configuration: registers the `gpu` marker, puts the repo root on sys.path and provides the
+golden fixtures.  `-m "not gpu"` must pass on a CPU-only box; `-m gpu` needs a B200."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+	sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+	config.addinivalue_line('markers', 'gpu: needs a CUDA device (B200); run with -m gpu')
+
+
+def load_golden(name):
+	with np.load(os.path.join(GOLDEN, name + '.npz')) as f:
+		return {k: f[k] for k in f.files}
+
+
+@pytest.fixture(scope = 'session')
+def golden():
+	return {name: load_golden(name) for name in ('solarsystem', 'galaxy256', 'galaxy4096')}
+
+
+@pytest.fixture(scope = 'session')
+def oracle():
+	from oracle import oracle as o
+	o.lib() # builds liboracle.so on first use
+	return o
+
+
+@pytest.fixture(scope = 'session')
+def shim():
+	from gravitation_b200 import _shim
+	_shim.load()
+	return _shim
