@@ -52,6 +52,8 @@ _SIGNATURES = [
 	('gravb200_variant_count', ctypes.c_int, [ctypes.c_int]),
 	('gravb200_variant_name', ctypes.c_char_p, [ctypes.c_int, ctypes.c_int]),
 	('gravb200_device_ptr', ctypes.c_void_p, [_c_ctx, ctypes.c_int]),
+	('gravb200_host_alloc', ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
+	('gravb200_host_free', ctypes.c_int, [ctypes.c_void_p]),
 	('gravb200_peak_probe', ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_int]),
 	]
 SYMBOLS = tuple(name for name, _, _ in _SIGNATURES)
@@ -116,6 +118,29 @@ def variant_names(dtype = 'float32'):
 	lib = load()
 	d = _DTYPES[dtype]
 	return [lib.gravb200_variant_name(d, i).decode() for i in range(lib.gravb200_variant_count(d))]
+
+
+class PinnedArray:
+	"""owner of a page-locked host buffer exposed as a numpy array (`.array`); freed with the object"""
+
+	def __init__(self, shape, dtype):
+		self._lib = load()
+		dt = np.dtype(dtype)
+		nbytes = int(np.prod(shape)) * dt.itemsize
+		p = ctypes.c_void_p()
+		_check(self._lib.gravb200_host_alloc(nbytes, ctypes.byref(p)))
+		self._p = p
+		buf = (ctypes.c_char * max(nbytes, 1)).from_address(p.value)
+		self.array = np.frombuffer(buf, dtype = dt, count = int(np.prod(shape))).reshape(shape)
+		self.array[...] = 0
+
+	def __del__(self):
+		try:
+			if self._p is not None and self._p.value:
+				self._lib.gravb200_host_free(self._p)
+				self._p = None
+		except Exception:
+			pass
 
 
 def _ptr(a):

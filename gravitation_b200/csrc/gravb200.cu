@@ -749,6 +749,17 @@ void* gravb200_device_ptr(gravb200_ctx* c, int which) {
     }
 }
 
+int gravb200_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(GRAVB200_EINVAL, "out is NULL");
+    *out = nullptr;
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return 0;
+}
+int gravb200_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
+    return 0;
+}
+
 int gravb200_peak_probe(int device, double* out, int n) {
     if (!out || n < 5) return fail(GRAVB200_EINVAL, "out needs room for 5 doubles");
     int ndev = 0;

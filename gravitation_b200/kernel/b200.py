@@ -167,10 +167,9 @@ class universe(universe_base):
 		self._eager = bool(self._meta.get('eager_host', False))
 		n = self.MASS_LEN
 		# host mirrors, laid out like the reference's numpy kernels (np2.py:63-66)
-		self.mass_r_array = np.zeros((n, 3), dtype = self.DTYPE)
-		self.mass_v_array = np.zeros((n, 3), dtype = self.DTYPE)
-		self.mass_a_array = np.zeros((n, 3), dtype = self.DTYPE)
-		self.mass_m_array = np.zeros((n,), dtype = self.DTYPE)
+		# (page-locked, so the on-demand downloads and `push_host_state` run at full PCIe rate)
+		self._pinned = [_shim.PinnedArray(shape, self.DTYPE) for shape in ((n, 3), (n, 3), (n, 3), (n,))]
+		self.mass_r_array, self.mass_v_array, self.mass_a_array, self.mass_m_array = (p.array for p in self._pinned)
 		if isinstance(self._mass_list, _bulk_masses):
 			self.mass_r_array[:, :] = self._bulk_r
 			self.mass_v_array[:, :] = self._bulk_v

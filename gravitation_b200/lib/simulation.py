@@ -75,7 +75,8 @@ def _star(rnd, n, stars_len, G, r0, v0, g_alpha, g_beta, m_hole, radius):
 			r_abs * math.sin(beta),
 			]
 	# circular orbit around the central mass, velocity at a right angle to the radius
-	v_abs = math.sqrt(G * m_hole / math.sqrt(r_s[0] ** 2 + r_s[1] ** 2 + r_s[2] ** 2))
+	# sum() on purpose: since Python 3.12 it is a compensated sum, and the reference calls it (`simulation.py:148`)
+	v_abs = math.sqrt(G * m_hole / math.sqrt(sum([d ** 2 for d in r_s])))
 	v_alpha = alpha - (math.pi / 2)
 	v_s = [v_abs * math.cos(v_alpha), v_abs * math.sin(v_alpha), 0.0]
 	# tilt by g_beta around x, turn by g_alpha around z (velocity, then position)

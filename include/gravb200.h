@@ -102,6 +102,10 @@ const char* gravb200_variant_name(int dtype, int variant);
  * which: 0 = pos front, 1 = pos back, 2 = vel front, 3 = acc. */
 void* gravb200_device_ptr(gravb200_ctx* ctx, int which);
 
+/* Page-locked host memory for the caller's mirrors (so uploads/downloads run at full PCIe rate). */
+int gravb200_host_alloc(size_t bytes, void** out);
+int gravb200_host_free(void* p);
+
 /* FP32/FP64 FMA-chain microbenchmark on `device` (measured non-tensor peak).
  * out[0] = fp32 FFMA TFLOP/s, out[1] = packed FFMA2 TFLOP/s, out[2] = fp64 DFMA TFLOP/s,
  * out[3] = MUFU.RSQ G op/s, out[4] = SM clock MHz observed during the fp32 run. */

@@ -1,0 +1,307 @@
+# -*- coding: utf-8 -*-
+"""GPU parity tests: the CUDA path, called through the C-ABI (gravitation_b200/_shim.py ->
+libgravb200.so) and through the reference-facing kernel module, against the oracle and the golden
+vectors generated from the reference.
+
+Tolerances (BASELINE.json north_star / SURVEY.md section 8d):
+  accelerations  max_i |a_i - a_ref_i| / |a_ref_i| <= 1e-4 (float32), <= 1e-11 (float64) vs a float64 reference
+  trajectories   after 10 steps, max_i |dr_i| / |r_i| and |dv_i| / |v_i| <= 5e-6 (float32), <= 1e-12 (float64)
+  stage 2        bit-exact against the oracle's separately-rounded restatement of np2.py:110-115
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_ACC = {'float32': 1e-4, 'float64': 1e-11}
+TOL_TRAJ = {'float32': 5e-6, 'float64': 1e-12}
+DTYPES = ('float32', 'float64')
+
+
+@pytest.fixture(scope = 'module')
+def gpu(shim):
+	if shim.device_count() < 1:
+		pytest.fail('no CUDA device: the gpu-marked tests must run on a B200 (there is no CPU fallback)')
+	return shim
+
+
+def run_stage1(gpu, r, v, m, G, T, dtype, eps = 0.0, variant = -1):
+	sh = gpu.Shard(r.shape[0], dtype)
+	try:
+		sh.upload(r, v, m, G, T, eps)
+		if variant >= 0:
+			sh.set_variant(variant)
+		sh.stage1()
+		sh.sync()
+		_, _, a = sh.download(r = False, v = False, a = True)
+		info = sh.info()
+	finally:
+		sh.close()
+	return a, info
+
+
+def traj_err(x, ref):
+	"""max_i |x_i - ref_i| / |ref_i|, body 0 of a galaxy sits at the origin: absolute, scaled by the
+	universe's extent"""
+	num = np.linalg.norm(x.astype(np.float64) - ref, axis = 1)
+	den = np.linalg.norm(ref, axis = 1)
+	den = np.where(den < 1e-6 * den.max(), den.max(), den)
+	return float(np.max(num / den))
+
+
+# ---- golden vectors from the reference -----------------------------------------------------------
+
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('case', ('solarsystem', 'galaxy256', 'galaxy4096'))
+def test_accelerations_match_reference_np2_float64(case, dtype, golden, oracle, gpu):
+	g = golden[case]
+	G, T = float(g['G']), float(g['T'])
+	r, v, m = g['r0'].astype(dtype), g['v0'].astype(dtype), g['m'].astype(dtype)
+	a, _ = run_stage1(gpu, r, v, m, G, T, dtype)
+	# vs the reference's own float64 result (includes the float32 rounding of the inputs)
+	assert oracle.max_rel_err(a, g['acc_np2_f64']) <= TOL_ACC[dtype]
+	# vs the oracle fed the SAME rounded inputs: isolates the arithmetic
+	assert oracle.max_rel_err(a, oracle.stage1_f64(r, m, G)) <= TOL_ACC[dtype]
+	if dtype == 'float32':
+		# and the CUDA path is at least as close to float64 as the reference's float32 kernels are (x4 slack)
+		ref_gap = max(oracle.max_rel_err(g['acc_np2_f32'], g['acc_np2_f64']), oracle.max_rel_err(g['acc_c1a'], g['acc_np2_f64']))
+		assert oracle.max_rel_err(a, g['acc_np2_f64']) <= 4 * ref_gap + 1e-6
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('case', ('solarsystem', 'galaxy256', 'galaxy4096'))
+def test_ten_step_trajectory_matches_reference(case, dtype, golden, gpu):
+	g = golden[case]
+	sh = gpu.Shard(g['r0'].shape[0], dtype)
+	sh.upload(g['r0'].astype(dtype), g['v0'].astype(dtype), g['m'].astype(dtype), float(g['G']), float(g['T']))
+	for _ in range(10):
+		sh.stage1(); sh.stage2()
+	r, v, _ = sh.download()
+	sh.close()
+	assert traj_err(r, g['r10_np2_f64']) <= TOL_TRAJ[dtype]
+	assert traj_err(v, g['v10_np2_f64']) <= TOL_TRAJ[dtype]
+
+
+# ---- oracle on seeded synthetic universes, ragged sizes ------------------------------------------
+
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('n', (2, 3, 5, 31, 257, 1000, 3001, 4099))
+def test_ragged_sizes_against_oracle(n, dtype, oracle, gpu):
+	r, v, m, G, T = oracle.uniform_universe(n, 1000 + n, dtype)
+	a, _ = run_stage1(gpu, r, v, m, G, T, dtype)
+	assert oracle.max_rel_err(a, oracle.stage1_f64(r, m, G)) <= TOL_ACC[dtype]
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_single_body_has_zero_acceleration(dtype, gpu):
+	r = np.array([[1.0, 2.0, 3.0]], dtype = dtype); v = np.array([[1.0, 0.0, 0.0]], dtype = dtype); m = np.array([5.0], dtype = dtype)
+	sh = gpu.Shard(1, dtype)
+	sh.upload(r, v, m, 1.0, 2.0)
+	sh.stage1(); sh.stage2()
+	rr, vv, aa = sh.download(a = True)
+	sh.close()
+	assert np.array_equal(aa, np.zeros((1, 3), dtype)) and np.array_equal(vv, v) and np.array_equal(rr, r + 2.0 * v)
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_every_kernel_variant_agrees_with_the_oracle(dtype, oracle, gpu):
+	n = 3001
+	r, v, m, G, T = oracle.uniform_universe(n, 7, dtype)
+	ref = oracle.stage1_f64(r, m, G)
+	names = gpu.variant_names(dtype)
+	for vi, name in enumerate(names):
+		a, info = run_stage1(gpu, r, v, m, G, T, dtype, variant = vi)
+		assert oracle.max_rel_err(a, ref) <= TOL_ACC[dtype], name
+		assert info['grid'] >= 1
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_softening_extension_against_oracle(dtype, oracle, gpu):
+	n = 777
+	r, v, m, G, T = oracle.uniform_universe(n, 3, dtype)
+	eps = 3.0e8
+	a, _ = run_stage1(gpu, r, v, m, G, T, dtype, eps = eps)
+	assert oracle.max_rel_err(a, oracle.stage1_f64(r, m, G, eps = eps)) <= TOL_ACC[dtype]
+	a0, _ = run_stage1(gpu, r, v, m, G, T, dtype)
+	assert not np.array_equal(a, a0)
+
+
+def test_coincident_distinct_bodies_are_not_masked(oracle, gpu):
+	"""the reference excludes only i == j (pc2.py:77): two different bodies at one point give a
+	non-finite acceleration there (rsqrt(0) = inf, 0 * inf = NaN, pc2.py:82-85) — not silently zero"""
+	r, v, m, G, T = oracle.uniform_universe(64, 5, 'float32')
+	r[10] = r[3]
+	a, _ = run_stage1(gpu, r, v, m, G, T, 'float32')
+	assert not np.isfinite(a[3]).all() and not np.isfinite(a[10]).all()
+	assert np.isfinite(np.delete(a, (3, 10), axis = 0)).all()
+
+
+# ---- stage semantics --------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_stage1_leaves_state_untouched_and_stage2_is_bit_exact(dtype, oracle, gpu):
+	n = 1531
+	r, v, m, G, T = oracle.uniform_universe(n, 11, dtype)
+	v = (np.random.default_rng(1).standard_normal((n, 3)) * 1e-5).astype(dtype)
+	sh = gpu.Shard(n, dtype)
+	sh.upload(r, v, m, G, T)
+	sh.stage1(); sh.sync()
+	r1, v1, a1 = sh.download(a = True)
+	assert np.array_equal(r1, r) and np.array_equal(v1, v) # front state unchanged between the stages
+	sh.stage2()
+	r2, v2, a2 = sh.download(a = True)
+	assert np.array_equal(a1, a2)
+	# np2.py:110-114 with separately rounded operations, applied on the host to the GPU's accelerations
+	r_ref, v_ref = r.copy(), v.copy()
+	oracle.stage2(r_ref, v_ref, a1, T)
+	assert np.array_equal(r2, r_ref) and np.array_equal(v2, v_ref)
+	with pytest.raises(gpu.GravB200Error, match = 'stage2 without a preceding stage1'):
+		sh.stage2()
+	sh.close()
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_steps_equals_repeated_stage_calls_and_is_deterministic(dtype, oracle, gpu):
+	n = 2048 + 77
+	r, v, m, G, T = oracle.uniform_universe(n, 21, dtype)
+	outs = []
+	for mode in ('stages', 'steps', 'steps'):
+		sh = gpu.Shard(n, dtype)
+		sh.upload(r, v, m, G, T)
+		if mode == 'stages':
+			for _ in range(5):
+				sh.stage1(); sh.stage2()
+		else:
+			sh.steps(5)
+		outs.append(sh.download(a = True))
+		sh.close()
+	for other in outs[1:]:
+		for x, y in zip(outs[0], other):
+			assert np.array_equal(x, y) # bit-identical: fixed-order combination of split i-blocks
+
+
+def test_upload_positions_only(oracle, gpu):
+	n = 500
+	r, v, m, G, T = oracle.uniform_universe(n, 2, 'float32')
+	sh = gpu.Shard(n, 'float32')
+	sh.upload(r, v, m, G, T)
+	r2 = (r * np.float32(0.5)).astype(np.float32)
+	sh.upload_positions(r2)
+	sh.stage1(); sh.sync()
+	_, _, a = sh.download(r = False, v = False, a = True)
+	sh.close()
+	assert oracle.max_rel_err(a, oracle.stage1_f64(r2, m, G)) <= 1e-4
+
+
+def test_argument_errors(gpu):
+	with pytest.raises(gpu.GravB200Error, match = 'n_total'):
+		gpu.Shard(0)
+	sh = gpu.Shard(8)
+	with pytest.raises(gpu.GravB200Error, match = 'no state uploaded'):
+		sh.stage1()
+	with pytest.raises(ValueError):
+		sh.upload(np.zeros((7, 3)), np.zeros((8, 3)), np.zeros(8), 1.0, 1.0)
+	sh.close()
+
+
+# ---- size-independent properties at BASELINE.json's sizes ----------------------------------------
+
+def test_full_size_2p16_all_rows_float32(oracle, gpu):
+	"""BASELINE.json configs[1]: 2^16 bodies fp32 on one B200, every row checked"""
+	n = 1 << 16
+	r, v, m, G, T = oracle.uniform_universe(n, 1016, 'float32')
+	a, info = run_stage1(gpu, r, v, m, G, T, 'float32')
+	assert oracle.max_rel_err(a, oracle.stage1_f64(r, m, G)) <= 1e-4
+	assert info['packed'] == 1 and info['grid'] == info['sm_count'] * info['ctas_per_sm']
+
+
+@pytest.mark.parametrize('dtype,n', (('float32', 1 << 20), ('float64', 1 << 18)))
+def test_full_size_properties(dtype, n, oracle, gpu):
+	"""north-star size (2^20 fp32) and configs[3] (2^18 fp64): sampled rows against the oracle plus
+	properties that need no reference: exact linearity in the masses / G, momentum balance"""
+	r, v, m, G, T = oracle.uniform_universe(n, 1000 + n.bit_length() - 1, dtype)
+	sh = gpu.Shard(n, dtype)
+	sh.upload(r, v, m, G, T)
+	sh.stage1(); sh.sync()
+	_, _, a = sh.download(r = False, v = False, a = True)
+	rows = np.linspace(0, n - 1, 1024).astype(np.int64)
+	assert oracle.max_rel_err(a[rows], oracle.stage1_f64(r, m, G, rows = rows)) <= TOL_ACC[dtype]
+	# Newton's third law: sum_i m_i a_i = 0 up to rounding
+	a64, m64 = a.astype(np.float64), m.astype(np.float64)
+	net = np.linalg.norm((a64 * m64[:, None]).sum(0)) / (np.linalg.norm(a64, axis = 1) * m64).sum()
+	assert net <= (1e-6 if dtype == 'float32' else 1e-13)
+	# doubling every mass (a power of two) must double every acceleration bit for bit; same for G
+	sh.upload(r, v, (m * 2).astype(dtype), G, T)
+	sh.stage1(); sh.sync()
+	_, _, a_m2 = sh.download(r = False, v = False, a = True)
+	assert np.array_equal(a_m2, a * np.array(2, dtype))
+	sh.close()
+
+
+# ---- through the reference-facing kernel module ---------------------------------------------------
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_kernel_module_front_end(dtype, golden, oracle, gpu):
+	from gravitation_b200.lib import simulation
+	from gravitation_b200.lib.load import inventory
+	kernel = inventory['b200']
+	kernel.load_module()
+	g = golden['galaxy256']
+	u = simulation.create_simulation('galaxy', kernel.get_class(), {'stars_len': 256, 'seed': 42, 'dtype': dtype})
+	assert len(u) == 256 and u._dtype == dtype
+	r0 = np.array([pm._r for pm in u])
+	assert np.array_equal(r0, g['r0'].astype(dtype))
+	u.step_stage1()
+	a = np.array([pm._a for pm in u]) # accelerations are readable between the stages
+	assert oracle.max_rel_err(a, g['acc_np2_f64']) <= TOL_ACC[dtype]
+	assert np.array_equal(np.array([pm._r for pm in u]), r0) # and positions have not moved yet
+	u.step_stage2(); u.step_stage3()
+	for _ in range(9):
+		u.step()
+	assert u._t == 10 * u._T
+	r10 = np.array([pm._r for pm in u]); v10 = np.array([pm._v for pm in u])
+	assert traj_err(r10, g['r10_np2_f64']) <= TOL_TRAJ[dtype] and traj_err(v10, g['v10_np2_f64']) <= TOL_TRAJ[dtype]
+	assert u._mass_list[0]._name == 'back hole' and float(u._mass_list[0]._m) == float(g['m'][0])
+	u.stop()
+	with pytest.raises(SyntaxError, match = 'simulation was stopped'):
+		u.step()
+
+
+def test_kernel_module_bulk_front_end_and_steps(oracle, gpu):
+	from gravitation_b200.kernel import b200
+	n = 5000
+	r, v, m, G, T = oracle.uniform_universe(n, 9, 'float64')
+	u = b200.universe(T = T, G = G, scale_off = True, dtype = 'float32')
+	u.add_objects(r, v, m, scale_off = True)
+	with pytest.raises(SyntaxError):
+		u.add_object(name = 'x', r = [0.0] * 3, v = [0.0] * 3, m = 1.0)
+	assert len(u) == n
+	u.start()
+	u.steps(3)
+	r3_ref, v3_ref = oracle.steps(r, v, m, G, T, 3)
+	assert traj_err(np.array([pm._r for pm in u]), r3_ref) <= 5e-6
+	assert traj_err(u._mass_list[n - 1]._r[None, :], r3_ref[n - 1:n]) <= 5e-6
+	assert u._t == 3 * T
+	u.stop()
+
+
+def test_multi_gpu_in_one_process_matches_single_gpu(oracle, gpu):
+	if gpu.device_count() < 2:
+		pytest.skip('needs 2 GPUs')
+	from gravitation_b200.kernel import b200
+	n = 10007
+	r, v, m, G, T = oracle.uniform_universe(n, 4, 'float64')
+	states = []
+	for gpus in (1, 2):
+		u = b200.universe(T = T, G = G, scale_off = True, dtype = 'float32', threads = gpus)
+		u.add_objects(r, v, m, scale_off = True)
+		u.start()
+		for _ in range(4):
+			u.step()
+		states.append((np.array([pm._r for pm in u]), np.array([pm._v for pm in u])))
+		u.stop()
+	# the shards sum their j-tiles in a different grouping, so agreement is to rounding, not bitwise
+	assert traj_err(states[1][0], states[0][0].astype(np.float64)) <= 1e-6
+	assert traj_err(states[1][1], states[0][1].astype(np.float64)) <= 1e-6
+	r4_ref, _ = oracle.steps(r, v, m, G, T, 4)
+	assert traj_err(states[1][0], r4_ref) <= 5e-6

@@ -1,0 +1,196 @@
+# -*- coding: utf-8 -*-
+"""CPU tests of the host side: front-end contract (mirrors /root/reference/src/gravitation/kernel/_base_.py),
+inventory, scenario builders against golden universes, and the C-ABI library's symbol table."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from gravitation_b200.kernel._base_ import universe_base, _point_mass
+from gravitation_b200.lib import load, simulation, timing
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class _noop(universe_base):
+	def step_stage1(self):
+		for pm in self._mass_list:
+			pm._a[:] = [1.0, 0.0, 0.0]
+
+
+# ---- universe_base contract (_base_.py:64-177) ---------------------------------------------------
+
+def test_constructor_scales_G_unless_scale_off():
+	u = _noop(G = 2.0, scale_m = 4.0, scale_r = 3.0)
+	assert u._G == 2.0 * 27.0 / 4.0
+	u = _noop(G = 2.0, scale_m = 4.0, scale_r = 3.0, scale_off = True, extra = 7)
+	assert u._G == 2.0 and u._meta == {'extra': 7}
+	assert (u._dtype, u._threads, u._t, u._T) == ('float32', 1, 0.0, 1.0e3)
+
+
+def test_add_object_scales_in_place_on_callers_lists():
+	u = _noop(scale_m = 0.5, scale_r = 10.0)
+	r, v = [1.0, 2.0, 3.0], [0.1, 0.2, 0.3]
+	u.add_object(name = 'a', r = r, v = v, m = 8.0)
+	assert r == [10.0, 20.0, 30.0] and v == [1.0, 2.0, 3.0] # caller's lists were modified (_base_.py:114-116)
+	pm = next(iter(u))
+	assert pm._m == 4.0 and pm._r is r and pm._a == [0.0, 0.0, 0.0] and len(u) == 1
+	u.add_object(name = 'b', r = [1.0, 1.0, 1.0], v = [0.0, 0.0, 0.0], m = 1.0, scale_off = True)
+	assert list(u)[1]._r == [1.0, 1.0, 1.0]
+
+
+def test_lifecycle_errors_have_the_reference_messages():
+	u = _noop()
+	with pytest.raises(SyntaxError, match = 'simulation was not started'):
+		u.step()
+	with pytest.raises(SyntaxError, match = 'simulation was not started'):
+		u.stop()
+	u.add_object(name = 'a', r = [0.0, 0.0, 0.0], v = [0.0, 0.0, 0.0], m = 1.0)
+	u.start()
+	with pytest.raises(SyntaxError, match = 'simulation is running'):
+		u.start()
+	with pytest.raises(SyntaxError, match = 'simulation was started'):
+		u.add_object(name = 'b', r = [0.0] * 3, v = [0.0] * 3, m = 1.0)
+	u.step()
+	u.stop()
+	for call, msg in ((u.step, 'simulation was stopped'), (u.start, 'simulation was stopped'), (u.stop, 'simulation was stopped before')):
+		with pytest.raises(SyntaxError, match = msg):
+			call()
+	with pytest.raises(SyntaxError, match = 'simulation was stopped'):
+		u.add_object(name = 'b', r = [0.0] * 3, v = [0.0] * 3, m = 1.0)
+
+
+def test_step_runs_three_stages_and_default_stage2_is_symplectic_euler():
+	u = _noop(T = 2.0)
+	u.add_object(name = 'a', r = [0.0, 0.0, 0.0], v = [1.0, 0.0, 0.0], m = 1.0)
+	u.start()
+	u.step()
+	pm = list(u)[0]
+	assert pm._v == [3.0, 0.0, 0.0] and pm._r == [6.0, 0.0, 0.0] and pm._a == [0.0, 0.0, 0.0] # new v moves r
+	assert u._t == 2.0
+	with pytest.raises(NotImplementedError):
+		universe_base().step_stage1()
+	assert str(pm).startswith('a | 6.0000e+00, 0.0000e+00')
+
+
+# ---- inventory (lib/load.py:40-107) --------------------------------------------------------------
+
+def test_inventory_lists_non_underscore_kernels_and_reads_meta_without_import():
+	assert 'b200' in load.inventory and not any(name.startswith('_') for name in load.inventory)
+	k = load.inventory['b200']
+	with pytest.raises(SyntaxError, match = 'metadata has not been loaded'):
+		k['parallel']
+	k.load_meta()
+	assert k['parallel'] is True and k['name'] == 'b200' and k['interpreters'] == ['python3']
+	assert set(load.META_KEYS) <= set(k.keys())
+	fresh = load._kernel(k._path, 'b200', True)
+	with pytest.raises(SyntaxError, match = 'module has not been loaded'):
+		fresh.get_class()
+	k.load_module()
+	assert k.get_class().__name__ == 'universe'
+
+
+def test_read_meta_ignores_non_name_targets():
+	meta = load.read_meta("__version__ = '1'\na.b = 3\nx, y = 1, 2\n__parallel__ = False\n")
+	assert meta['version'] == '1' and meta['parallel'] is False and meta['longname'] is None
+
+
+# ---- scenario builders (lib/simulation.py:41-184) ------------------------------------------------
+
+class _recorder(universe_base):
+	def step_stage1(self):
+		pass
+
+
+def _state(u):
+	r = np.array([list(pm._r) for pm in u]); v = np.array([list(pm._v) for pm in u]); m = np.array([pm._m for pm in u])
+	return r, v, m
+
+
+@pytest.mark.parametrize('case,n', (('galaxy256', 256), ('galaxy4096', 4096)))
+def test_seeded_galaxy_equals_the_reference_universe(case, n, golden):
+	g = golden[case]
+	u = simulation.create_simulation('galaxy', _recorder, {'stars_len': n, 'seed': 42, 'dtype': 'float64'})
+	r, v, m = _state(u)
+	assert len(u) == n and list(u)[0]._name == 'back hole' and list(u)[1]._name == 'star'
+	assert np.array_equal(r, g['r0']) and np.array_equal(v, g['v0']) and np.array_equal(m, g['m'])
+	assert u._G == float(g['G']) and u._T == 2.0e12 and u._screen['unit'] == 1e20
+
+
+def test_unseeded_galaxy_uses_the_global_random_stream_like_the_reference(golden):
+	import random
+	random.seed(42)
+	u = simulation.create_simulation('galaxy', _recorder, {'stars_len': 256, 'dtype': 'float64'})
+	assert np.array_equal(_state(u)[0], golden['galaxy256']['r0'])
+
+
+def test_solarsystem_and_unknown_scenario(golden):
+	u = simulation.create_simulation('solarsystem', _recorder, {'dtype': 'float64'})
+	r, v, m = _state(u)
+	g = golden['solarsystem']
+	assert np.array_equal(r, g['r0']) and np.array_equal(v, g['v0']) and np.array_equal(m, g['m'])
+	with pytest.raises(ValueError, match = 'Unknown scenario'):
+		simulation.create_simulation('nope', _recorder)
+
+
+def test_snapshot_roundtrip(tmp_path):
+	u = simulation.create_simulation('galaxy', _recorder, {'stars_len': 32, 'seed': 1})
+	fn = str(tmp_path / 'data.h5')
+	path = simulation.store_simulation(u, fn, 'kernel=x;len=32;step=0')
+	u2 = simulation.load_simulation(_recorder, path, 'kernel=x;len=32;step=0')
+	r, v, m = _state(u); r2, v2, m2 = _state(u2)
+	assert np.array_equal(r.astype('f4'), r2.astype('f4')) and np.array_equal(m.astype('f4'), m2.astype('f4'))
+	assert u2._G == u._G and u2._T == u._T and u2._dtype == 'float32' and list(u2)[0]._name == 'back hole'
+
+
+def test_timers():
+	t = timing.best_run_timer()
+	for _ in range(3):
+		t.start(); t.stop()
+	assert len(t) == 3 and t.min() <= t.avg() <= t.sum() and timing.elapsed_timer()() >= 0
+
+
+# ---- C-ABI library: loads, exports everything the header declares, refuses to compute without a GPU
+
+def test_library_exports_every_symbol_of_the_header(shim):
+	header = open(os.path.join(ROOT, 'include', 'gravb200.h')).read()
+	declared = set(re.findall(r'\b(gravb200_[a-z0-9_]+)\s*\(', header))
+	assert declared == set(shim.SYMBOLS)
+	lib = shim.load()
+	for name in declared:
+		assert hasattr(lib, name)
+	assert lib.gravb200_abi_version() == 1
+	assert lib.gravb200_variant_count(shim.F32) >= 4 and lib.gravb200_variant_count(shim.F64) >= 3
+
+
+def test_no_cpu_fallback(shim):
+	if shim.device_count() > 0:
+		pytest.skip('a GPU is present')
+	with pytest.raises(shim.GravB200Error, match = 'no CUDA device'):
+		shim.Shard(16)
+	from gravitation_b200.kernel import b200
+	u = b200.universe()
+	u.add_object(name = 'a', r = [0.0] * 3, v = [0.0] * 3, m = 1.0)
+	with pytest.raises(shim.GravB200Error):
+		u.start()
+
+
+def test_product_code_never_touches_the_oracle():
+	for base, _, files in os.walk(os.path.join(ROOT, 'gravitation_b200')):
+		for fn in files:
+			if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+				src = open(os.path.join(base, fn), errors = 'replace').read()
+				assert not re.search(r'^\s*(from|import)\s+oracle|liboracle|oracle/_ref', src, re.M), fn
+
+
+def test_row_partition_covers_all_rows():
+	from gravitation_b200.dist import row_partition
+	for n, world in ((1 << 20, 8), (5, 8), (1000, 3), (7, 1)):
+		parts = row_partition(n, world)
+		assert len(parts) == world and sum(c for _, c in parts) == n
+		pos = 0
+		for row0, cnt in parts:
+			if cnt:
+				assert row0 == pos
+			pos += cnt
