@@ -377,7 +377,7 @@ int download_impl(gravb200_ctx* c, void* r, void* v, void* a) {
 // peak probe kernels (a measured non-tensor FP32/FP64 peak for the roofline)
 // ---------------------------------------------------------------------------------------------
 constexpr int kProbeIters = 4096;
-constexpr int kProbeChains = 8;
+constexpr int kProbeChains = 12;   // independent chains per thread (latency 4, issue every 1-2 cycles)
 
 __global__ void probe_ffma(float* out, float a, float b, unsigned long long* clk) {
     float x[kProbeChains];
@@ -387,7 +387,7 @@ __global__ void probe_ffma(float* out, float a, float b, unsigned long long* clk
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
     for (int i = 0; i < kProbeIters; ++i) {
 #pragma unroll
-        for (int c = 0; c < kProbeChains; ++c) x[c] = fmaf(x[c], a, b);
+        for (int c = 0; c < kProbeChains; ++c) x[c] = fmaf(x[c], a, a);   // 2 distinct registers: not operand-fetch bound
     }
     unsigned long long t1 = clock64(), g1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
@@ -404,7 +404,7 @@ __global__ void probe_ffma2(float* out, float a, float b) {
     const float2 a2 = make_float2(a, a * 1.0001f), b2 = make_float2(b, b * 0.999f);
     for (int i = 0; i < kProbeIters; ++i) {
 #pragma unroll
-        for (int c = 0; c < kProbeChains; ++c) x[c] = __ffma2_rn(x[c], a2, b2);
+        for (int c = 0; c < kProbeChains; ++c) x[c] = __ffma2_rn(x[c], a2, a2);   // 2 distinct register pairs (3 pairs would cost 3 cycles)
     }
     float s = 0;
 #pragma unroll
@@ -417,7 +417,7 @@ __global__ void probe_dfma(double* out, double a, double b) {
     for (int c = 0; c < kProbeChains; ++c) x[c] = (double)(threadIdx.x + c);
     for (int i = 0; i < kProbeIters; ++i) {
 #pragma unroll
-        for (int c = 0; c < kProbeChains; ++c) x[c] = fma(x[c], a, b);
+        for (int c = 0; c < kProbeChains; ++c) x[c] = fma(x[c], a, a);
     }
     double s = 0;
 #pragma unroll
