@@ -16,6 +16,8 @@ import numpy as np
 
 F32, F64 = 0, 1
 NCCL_ID_BYTES = 128
+PEER_BLOB_BYTES = 256
+XCHG_NCCL, XCHG_PEER = 0, 1
 _DTYPES = {'float32': F32, 'float64': F64}
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libgravb200.so')
@@ -42,6 +44,9 @@ _SIGNATURES = [
 	('gravb200_exchange', ctypes.c_int, [_c_ctx]),
 	('gravb200_group_begin', ctypes.c_int, []),
 	('gravb200_group_end', ctypes.c_int, []),
+	('gravb200_peer_export', ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
+	('gravb200_peer_connect', ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
+	('gravb200_set_exchange_mode', ctypes.c_int, [_c_ctx, ctypes.c_int]),
 	('gravb200_steps', ctypes.c_int, [_c_ctx, ctypes.c_int]),
 	('gravb200_sync', ctypes.c_int, [_c_ctx]),
 	('gravb200_download', ctypes.c_int, [_c_ctx, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -194,6 +199,21 @@ class Shard:
 	def stage1(self):
 		_check(self._lib.gravb200_stage1(self._ctx))
 
+	def peer_export(self):
+		buf = ctypes.create_string_buffer(PEER_BLOB_BYTES)
+		_check(self._lib.gravb200_peer_export(self._ctx, buf))
+		return buf.raw
+
+	def peer_connect(self, blobs):
+		"""blobs: the `peer_export()` of every shard, in rank order"""
+		joined = b''.join(bytes(b) for b in blobs)
+		if len(joined) != PEER_BLOB_BYTES * self.world:
+			raise ValueError('need %d blobs of %d bytes' % (self.world, PEER_BLOB_BYTES))
+		_check(self._lib.gravb200_peer_connect(self._ctx, ctypes.create_string_buffer(joined, len(joined))))
+
+	def set_exchange_mode(self, mode):
+		_check(self._lib.gravb200_set_exchange_mode(self._ctx, int(mode)))
+
 	def exchange(self):
 		_check(self._lib.gravb200_exchange(self._ctx))
 
@@ -228,9 +248,9 @@ class Shard:
 		return dict(sweep_ms = ms[0], exchange_ms = ms[1], steps_ms = ms[2], sm_mhz = ms[3])
 
 	def info(self):
-		v = (ctypes.c_int64 * 10)()
-		_check(self._lib.gravb200_info(self._ctx, v, 10))
-		keys = ('grid', 'threads', 'bodies_per_thread', 'tile', 'stages', 'smem_bytes', 'launches', 'sm_count', 'packed', 'ctas_per_sm')
+		v = (ctypes.c_int64 * 11)()
+		_check(self._lib.gravb200_info(self._ctx, v, 11))
+		keys = ('grid', 'threads', 'bodies_per_thread', 'tile', 'stages', 'smem_bytes', 'launches', 'sm_count', 'packed', 'ctas_per_sm', 'exchange_mode')
 		return dict(zip(keys, [int(x) for x in v]))
 
 	def set_variant(self, variant):

@@ -16,6 +16,8 @@
 #include <dlfcn.h>
 #include <nccl.h>   // types only; the library is dlopen'ed so single-GPU use needs no NCCL
 
+#include <unistd.h>
+
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -102,21 +104,21 @@ struct Variant {
     const void* fn;
 };
 
-template <typename REAL, int THREADS, int R, int TILE, int STAGES, int MINB, int PACK, int UNROLL, int PREF>
+template <typename REAL, int THREADS, int R, int TILE, int STAGES, int MINB, int PACK, int UNROLL, int SS>
 Variant make_variant(const char* name) {
     Variant v;
     v.name = name;
     v.threads = THREADS; v.r = R; v.tile = TILE; v.stages = STAGES; v.minb = MINB; v.pack = PACK;
-    v.smem = sweep_smem_bytes<REAL, THREADS, R, TILE, STAGES>();
-    v.fn = (const void*)&sweep_kernel<REAL, THREADS, R, TILE, STAGES, MINB, PACK, UNROLL, PREF>;
+    v.smem = sweep_smem_bytes<REAL, THREADS, R, TILE, STAGES, SS>();
+    v.fn = (const void*)&sweep_kernel<REAL, THREADS, R, TILE, STAGES, MINB, PACK, UNROLL, SS>;
     return v;
 }
 
 // Ordered large -> small work granularity; the automatic choice takes the first one that still
 // gives every resident CTA >= 8 tiles (see pick_variant).  Entries after the "auto" prefix are
 // only reachable through gravb200_set_variant (ncu A/B evidence, tuning sweeps).
-#define V32(T, R, TILE, ST, MB, PK, U, PF) \
-    make_variant<float, T, R, TILE, ST, MB, PK, U, PF>("f32_t" #T "_r" #R "_j" #TILE "_s" #ST "_b" #MB "_p" #PK "_u" #U "_f" #PF)
+#define V32(T, R, TILE, ST, MB, PK, U, SS) \
+    make_variant<float, T, R, TILE, ST, MB, PK, U, SS>("f32_t" #T "_r" #R "_j" #TILE "_s" #ST "_b" #MB "_p" #PK "_u" #U "_m" #SS)
 #define V64(T, R, TILE, ST, MB, U) \
     make_variant<double, T, R, TILE, ST, MB, 0, U, 0>("f64_t" #T "_r" #R "_j" #TILE "_s" #ST "_b" #MB "_u" #U)
 
@@ -128,18 +130,18 @@ const std::vector<Variant>& variants_f32() {
         V32(128, 2, 64, 4, 4, 1, 2, 0),     // 3  auto: tiny N    (IBLK 256)
         V32(256, 8, 512, 3, 1, 0, 2, 0),    // 4  scalar-FFMA twin of 0 (A/B evidence)
         V32(512, 4, 512, 3, 1, 1, 2, 0),    // 5
-        V32(256, 8, 512, 3, 1, 1, 2, 1),    // 6  0 + prefetch
-        V32(512, 4, 512, 3, 1, 1, 2, 1),    // 7  5 + prefetch
-        V32(384, 8, 512, 3, 1, 1, 2, 0),    // 8
-        V32(384, 8, 512, 3, 1, 1, 2, 1),    // 9
-        V32(320, 8, 512, 3, 1, 1, 2, 0),    // 10
-        V32(320, 8, 512, 3, 1, 1, 2, 1),    // 11
-        V32(256, 8, 512, 3, 1, 1, 1, 1),    // 12
+        V32(256, 8, 512, 3, 1, 1, 2, 1),    // 6  0 with shared-memory sums
+        V32(384, 8, 512, 3, 1, 1, 2, 1),    // 7
+        V32(512, 8, 512, 3, 1, 1, 2, 1),    // 8
+        V32(512, 8, 512, 3, 1, 1, 1, 1),    // 9
+        V32(384, 8, 512, 3, 1, 1, 1, 1),    // 10
+        V32(512, 6, 512, 3, 1, 1, 2, 1),    // 11
+        V32(512, 4, 512, 3, 1, 1, 2, 1),    // 12
         V32(256, 8, 512, 3, 1, 1, 4, 1),    // 13
-        V32(512, 4, 512, 3, 1, 1, 4, 1),    // 14
-        V32(384, 6, 512, 3, 1, 1, 2, 1),    // 15
-        V32(256, 10, 512, 3, 1, 1, 2, 0),   // 16
-        V32(256, 10, 512, 3, 1, 1, 2, 1),   // 17
+        V32(384, 6, 512, 3, 1, 1, 2, 1),    // 14
+        V32(256, 12, 512, 3, 1, 1, 2, 1),   // 15
+        V32(256, 8, 512, 3, 2, 1, 2, 1),    // 16
+        V32(128, 8, 512, 3, 3, 1, 2, 1),    // 17
     };
     return v;
 }
@@ -147,12 +149,12 @@ constexpr int kAutoF32 = 4;
 
 const std::vector<Variant>& variants_f64() {
     static const std::vector<Variant> v = {
-        V64(256, 2, 256, 3, 2, 2),   // 0 auto: large N
+        V64(256, 2, 256, 3, 2, 4),   // 0 auto: large N
         V64(128, 2, 128, 3, 4, 2),   // 1 auto
         V64(128, 1, 64, 4, 4, 2),    // 2 auto: tiny N
         V64(256, 4, 256, 3, 2, 2),   // 3
         V64(512, 2, 256, 3, 1, 2),   // 4
-        V64(256, 2, 256, 3, 2, 4),   // 5
+        V64(256, 2, 256, 3, 2, 2),   // 5
         V64(256, 2, 256, 3, 2, 1),   // 6
         V64(512, 1, 256, 3, 2, 2),   // 7
     };
@@ -217,6 +219,14 @@ struct gravb200_ctx {
     int forced_variant = -1;
     int variant = 0, grid = 0, occ = 0;
     int64_t launches = 0;
+    // peer-store exchange (multi-GPU): NVLink-mapped views of every peer's position buffers and flags
+    bool peer_connected = false, peer_mode = false;
+    unsigned long long* flags = nullptr;          // [kMaxPeers + 1], written by the peers
+    int* xerr = nullptr;                          // device flag: barrier timed out
+    void* peer_pos[2][kMaxPeers + 1] = {};
+    unsigned long long* peer_flags[kMaxPeers + 1] = {};
+    bool peer_is_ipc[kMaxPeers + 1] = {};
+    unsigned long long epoch = 0;                 // barrier generation, advanced in lockstep on all ranks
 };
 
 namespace {
@@ -306,14 +316,43 @@ int launch_sweep(gravb200_ctx* c, int integrate) {
     p.eps2_d = c->eps * c->eps;
     p.integrate = integrate;
     p.clk = c->clk;
+    p.n_peers = 0;
+    if (c->peer_mode) {
+        for (int q = 0; q < c->world; ++q)
+            if (q != c->rank) p.peer_back[p.n_peers++] = c->peer_pos[c->front ^ 1][q];
+    }
     void* args[] = {&p};
     CU(cudaLaunchKernel(v.fn, dim3(c->grid), dim3(v.threads), args, v.smem, c->stream));
     c->launches++;
     return 0;
 }
 
+int peer_barrier(gravb200_ctx* c) {
+    BarrierParams b;
+    b.my_flags = c->flags;
+    for (int q = 0; q < c->world; ++q) b.peer_flags[q] = c->peer_flags[q];
+    b.rank = c->rank;
+    b.world = c->world;
+    b.step = ++c->epoch;
+    b.timeout_ns = 60ull * 1000 * 1000 * 1000;
+    b.error = c->xerr;
+    exchange_barrier_kernel<<<1, 32, 0, c->stream>>>(b);
+    CU(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int check_barrier_error(gravb200_ctx* c) {
+    if (!c->peer_mode) return 0;
+    int e = 0;
+    CU(cudaMemcpy(&e, c->xerr, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e) return fail(GRAVB200_ECUDA, "peer-store exchange: a peer GPU did not reach the step barrier within 60 s");
+    return 0;
+}
+
 int exchange(gravb200_ctx* c) {
     if (c->world == 1) return 0;
+    if (c->peer_mode) return peer_barrier(c);   // the data already travelled in the sweep's epilogue
     char* back = (char*)c->pos[c->front ^ 1];
     const size_t count = (size_t)c->chunk * 4;   // scalars per shard
     NC(g_nccl.AllGather(back + (size_t)c->rank * c->chunk * 4 * c->esz, back, count,
@@ -489,6 +528,7 @@ int gravb200_ctx_create(int64_t n_total, int dtype, int device, int rank, int wo
     if (dtype != GRAVB200_F32 && dtype != GRAVB200_F64) return fail(GRAVB200_EINVAL, "unknown dtype %d", dtype);
     if (world < 1 || rank < 0 || rank >= world) return fail(GRAVB200_EINVAL, "bad rank/world %d/%d", rank, world);
     if (world > 1 && !nccl_id) return fail(GRAVB200_EINVAL, "world > 1 needs an NCCL unique id");
+    if (world > kMaxPeers + 1) return fail(GRAVB200_EINVAL, "world %d exceeds the supported %d GPUs", world, kMaxPeers + 1);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -537,6 +577,10 @@ int gravb200_ctx_create(int64_t n_total, int dtype, int device, int rank, int wo
     CUX(cudaMalloc(&c->stage3, (size_t)n_total * 3 * c->esz));
     CUX(cudaMalloc(&c->stagem, (size_t)n_total * c->esz));
     CUX(cudaMalloc(&c->clk, 2 * sizeof(unsigned long long)));
+    CUX(cudaMalloc(&c->flags, (kMaxPeers + 1) * sizeof(unsigned long long)));
+    CUX(cudaMemsetAsync(c->flags, 0, (kMaxPeers + 1) * sizeof(unsigned long long), c->stream));
+    CUX(cudaMalloc(&c->xerr, sizeof(int)));
+    CUX(cudaMemsetAsync(c->xerr, 0, sizeof(int), c->stream));
     CUX(cudaMemsetAsync(c->clk, 0, 2 * sizeof(unsigned long long), c->stream));
 #undef CUX
     if (world > 1) {
@@ -571,6 +615,14 @@ int gravb200_ctx_destroy(gravb200_ctx* c) {
     if (c->stage3) cudaFree(c->stage3);
     if (c->stagem) cudaFree(c->stagem);
     if (c->clk) cudaFree(c->clk);
+    for (int q = 0; q <= kMaxPeers; ++q) {
+        if (!c->peer_is_ipc[q]) continue;
+        for (int b = 0; b < 2; ++b)
+            if (c->peer_pos[b][q]) cudaIpcCloseMemHandle(c->peer_pos[b][q]);
+        if (c->peer_flags[q]) cudaIpcCloseMemHandle(c->peer_flags[q]);
+    }
+    if (c->flags) cudaFree(c->flags);
+    if (c->xerr) cudaFree(c->xerr);
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -590,6 +642,9 @@ int gravb200_upload(gravb200_ctx* c, const void* r, const void* v, const void* m
     // masses travel in .w of both buffers: copy front -> back once so the epilogue's w is consistent
     CU(cudaMemcpyAsync(c->pos[c->front ^ 1], c->pos[c->front], (size_t)c->n_pad * 4 * c->esz,
                        cudaMemcpyDeviceToDevice, c->stream));
+    // peer-store mode: nobody may start writing r' into this GPU's back buffer before the copy above
+    // is done everywhere (every rank calls upload, so the barrier generations stay in lockstep)
+    if (c->peer_mode) { rc = peer_barrier(c); if (rc) return rc; }
     CU(cudaStreamSynchronize(c->stream));
     c->uploaded = true;
     return 0;
@@ -657,7 +712,7 @@ int gravb200_stage2(gravb200_ctx* c) {
     CU(cudaStreamSynchronize(c->stream));
     c->front ^= 1;
     c->pending = false;
-    return 0;
+    return check_barrier_error(c);
 }
 
 int gravb200_steps(gravb200_ctx* c, int k) {
@@ -678,7 +733,7 @@ int gravb200_steps(gravb200_ctx* c, int k) {
     CU(cudaStreamSynchronize(c->stream));
     c->ev_sweep = false;
     c->ev_steps = true;
-    return 0;
+    return check_barrier_error(c);
 }
 
 int gravb200_sync(gravb200_ctx* c) {
@@ -720,9 +775,9 @@ int gravb200_timings(gravb200_ctx* c, float* ms, int n) {
 int gravb200_info(const gravb200_ctx* c, int64_t* info, int n) {
     if (!c || !info) return fail(GRAVB200_EINVAL, "ctx / info is NULL");
     const Variant& v = variants_of(c->dtype)[c->variant];
-    const int64_t vals[10] = {c->grid, v.threads, v.r, v.tile, v.stages, (int64_t)v.smem,
-                              c->launches, c->sm_count, v.pack, c->occ};
-    for (int i = 0; i < n && i < 10; ++i) info[i] = vals[i];
+    const int64_t vals[11] = {c->grid, v.threads, v.r, v.tile, v.stages, (int64_t)v.smem,
+                              c->launches, c->sm_count, v.pack, c->occ, c->peer_mode ? 1 : 0};
+    for (int i = 0; i < n && i < 11; ++i) info[i] = vals[i];
     return 0;
 }
 
@@ -747,6 +802,86 @@ void* gravb200_device_ptr(gravb200_ctx* c, int which) {
         case 3: return c->acc;
         default: return nullptr;
     }
+}
+
+namespace {
+struct PeerBlob {   // what one shard publishes to the others (GRAVB200_PEER_BLOB_BYTES)
+    int32_t pid, device, rank, world;
+    uint64_t pos[2], flags;   // raw device pointers, meaningful inside the owner's process
+    cudaIpcMemHandle_t h_pos[2], h_flags;
+};
+static_assert(sizeof(PeerBlob) <= GRAVB200_PEER_BLOB_BYTES, "peer blob size");
+}  // namespace
+
+int gravb200_peer_export(gravb200_ctx* c, void* blob) {
+    if (!c || !blob) return fail(GRAVB200_EINVAL, "ctx / blob is NULL");
+    CU(cudaSetDevice(c->device));
+    PeerBlob b;
+    memset(&b, 0, sizeof(b));
+    b.pid = (int32_t)getpid();
+    b.device = c->device;
+    b.rank = c->rank;
+    b.world = c->world;
+    b.pos[0] = (uint64_t)c->pos[0];
+    b.pos[1] = (uint64_t)c->pos[1];
+    b.flags = (uint64_t)c->flags;
+    CU(cudaIpcGetMemHandle(&b.h_pos[0], c->pos[0]));
+    CU(cudaIpcGetMemHandle(&b.h_pos[1], c->pos[1]));
+    CU(cudaIpcGetMemHandle(&b.h_flags, c->flags));
+    memset(blob, 0, GRAVB200_PEER_BLOB_BYTES);
+    memcpy(blob, &b, sizeof(b));
+    return 0;
+}
+
+int gravb200_peer_connect(gravb200_ctx* c, const void* blobs) {
+    if (!c || !blobs) return fail(GRAVB200_EINVAL, "ctx / blobs is NULL");
+    if (c->world == 1) return 0;
+    if (c->pending) return fail(GRAVB200_EINVAL, "cannot connect peers between stage1 and stage2");
+    CU(cudaSetDevice(c->device));
+    const int32_t mypid = (int32_t)getpid();
+    for (int q = 0; q < c->world; ++q) {
+        PeerBlob b;
+        memcpy(&b, (const char*)blobs + (size_t)q * GRAVB200_PEER_BLOB_BYTES, sizeof(b));
+        if (b.rank != q || b.world != c->world) return fail(GRAVB200_EINVAL, "peer blob %d is from rank %d of %d", q, b.rank, b.world);
+        if (q == c->rank) {
+            c->peer_pos[0][q] = c->pos[0]; c->peer_pos[1][q] = c->pos[1]; c->peer_flags[q] = c->flags;
+            continue;
+        }
+        if (b.pid == mypid) {
+            // same process: plain peer access to the other context's allocations
+            if (b.device != c->device) {
+                int can = 0;
+                CU(cudaDeviceCanAccessPeer(&can, c->device, b.device));
+                if (!can) return fail(GRAVB200_ECUDA, "GPU %d cannot access GPU %d", c->device, b.device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(GRAVB200_ECUDA, "cudaDeviceEnablePeerAccess(%d): %s", b.device, cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            c->peer_pos[0][q] = (void*)b.pos[0]; c->peer_pos[1][q] = (void*)b.pos[1];
+            c->peer_flags[q] = (unsigned long long*)b.flags;
+            c->peer_is_ipc[q] = false;
+        } else {
+            void* p0 = nullptr; void* p1 = nullptr; void* pf = nullptr;
+            CU(cudaIpcOpenMemHandle(&p0, b.h_pos[0], cudaIpcMemLazyEnablePeerAccess));
+            CU(cudaIpcOpenMemHandle(&p1, b.h_pos[1], cudaIpcMemLazyEnablePeerAccess));
+            CU(cudaIpcOpenMemHandle(&pf, b.h_flags, cudaIpcMemLazyEnablePeerAccess));
+            c->peer_pos[0][q] = p0; c->peer_pos[1][q] = p1; c->peer_flags[q] = (unsigned long long*)pf;
+            c->peer_is_ipc[q] = true;
+        }
+    }
+    c->peer_connected = true;
+    return 0;
+}
+
+int gravb200_set_exchange_mode(gravb200_ctx* c, int mode) {
+    if (!c) return fail(GRAVB200_EINVAL, "ctx is NULL");
+    if (mode != GRAVB200_XCHG_NCCL && mode != GRAVB200_XCHG_PEER) return fail(GRAVB200_EINVAL, "unknown exchange mode %d", mode);
+    if (c->pending) return fail(GRAVB200_EINVAL, "cannot switch the exchange between stage1 and stage2");
+    if (mode == GRAVB200_XCHG_PEER && c->world > 1 && !c->peer_connected)
+        return fail(GRAVB200_EINVAL, "peer-store exchange needs gravb200_peer_connect first");
+    c->peer_mode = (mode == GRAVB200_XCHG_PEER) && c->world > 1;
+    return 0;
 }
 
 int gravb200_host_alloc(size_t bytes, void** out) {

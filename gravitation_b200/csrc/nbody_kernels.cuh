@@ -29,6 +29,8 @@
 
 namespace gravb200 {
 
+constexpr int kMaxPeers = 15;   // one 16-GPU NVSwitch domain at most
+
 struct SweepParams {
     const void* pos_front;    // [n_pad] {x,y,z,m} of ALL bodies (read)
     void* pos_back;           // [n_pad] same layout; local rows written by the epilogue
@@ -47,6 +49,10 @@ struct SweepParams {
     double eps2_d;            // softening^2 (fp64 kernel)
     int integrate;            // 1: epilogue also writes vel_back / pos_back
     unsigned long long* clk;  // optional [2]: CTA 0 writes {SM cycles, ns} of its lifetime (clock evidence)
+    // fused position exchange (multi-GPU, peer-store mode): the epilogue also stores r' into the back
+    // position buffer of every peer GPU through NVLink-mapped pointers (no collective launch)
+    int n_peers;
+    void* peer_back[kMaxPeers];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -97,6 +103,18 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // one MUFU.RSQ, 2 ulp
     return y;
 }
+// m * d2^(-3/2) in fp64 without the math library's rsqrt(): MUFU.RSQ64H seed y0 (relative error
+// <= 2^-22), residual e = 1 - d2*y0^2, then d2^(-3/2) = y0^3 * (1 - e)^(-3/2) = y0^3 * (1 + 3/2 e +
+// 15/8 e^2 + O(e^3)); the dropped term is < 2^-60.  7 FP64-pipe operations, branch free (rsqrt() costs 5
+// plus a range-check branch, and the cube and mass 3 more).  d2 = 0 gives NaN, like inf * 0 in the reference.
+__device__ __forceinline__ double mass_over_r3(double m, double d2) {
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d2));
+    const double q = y0 * y0;
+    const double e = fma(-d2, q, 1.0);
+    const double c = fma(fma(e, 1.875, 1.5), e, 1.0);
+    return ((m * y0) * q) * c;
+}
 __device__ __forceinline__ double ld_cg_f64(const double* p) {
     double v;
     asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
@@ -135,6 +153,7 @@ __device__ __forceinline__ void finalize_body(const SweepParams& p, long long i_
         ri.z = __fadd_rn(ri.z, __fmul_rn(v.z, T));
         ((float4*)p.vel_back)[i_local] = v;
         ((float4*)p.pos_back)[p.row0 + i_local] = ri;
+        for (int q = 0; q < p.n_peers; ++q) ((float4*)p.peer_back[q])[p.row0 + i_local] = ri;   // NVLink peer store
     }
 }
 __device__ __forceinline__ void finalize_body(const SweepParams& p, long long i_local, double sx,
@@ -152,6 +171,7 @@ __device__ __forceinline__ void finalize_body(const SweepParams& p, long long i_
         ri.z = __dadd_rn(ri.z, __dmul_rn(v.z, T));
         ((double4*)p.vel_back)[i_local] = v;
         ((double4*)p.pos_back)[p.row0 + i_local] = ri;
+        for (int q = 0; q < p.n_peers; ++q) ((double4*)p.peer_back[q])[p.row0 + i_local] = ri;   // NVLink peer store
     }
 }
 
@@ -162,21 +182,24 @@ __device__ __forceinline__ void finalize_body(const SweepParams& p, long long i_
 //   i-block;  TILE j-bodies per shared-memory stage;  STAGES ring depth;  MINB min CTAs per SM.
 //   PACK    fp32 only: 1 = packed f32x2 over i-body pairs, 0 = scalar FFMA (kept for the ncu A/B).
 //   UNROLL  j-bodies per trip of the inner loop.
-//   PREF    fp32 packed path: 1 = explicit register prefetch of the next trip's j-bodies.
-// Shared memory (dynamic): STAGES*TILE*sizeof(vec4) tile ring, then 2*STAGES mbarriers.
+//   SS      fp32 packed path: 1 = the per-thread fp64 sums live in shared memory instead of registers.
+// Shared memory (dynamic): STAGES*TILE*sizeof(vec4) tile ring, 2*STAGES mbarriers, then (SS) 3*R*THREADS doubles.
 // ------------------------------------------------------------------------------------------------
-template <typename REAL, int THREADS, int R, int TILE, int STAGES, int MINB, int PACK, int UNROLL, int PREF>
+template <typename REAL, int THREADS, int R, int TILE, int STAGES, int MINB, int PACK, int UNROLL, int SS>
 __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams p) {
     using V4 = typename Vec4<REAL>::type;
     constexpr int IBLK = THREADS * R;
     constexpr int NWARPS = THREADS / 32;
     constexpr bool F32 = sizeof(REAL) == 4;
     static_assert(!F32 || (R % 2 == 0), "fp32 path packs pairs of i-bodies");
+    static_assert(!SS || (F32 && PACK), "shared-memory sums exist for the packed fp32 path only");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     V4* tiles = reinterpret_cast<V4*>(smem_raw);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * TILE * sizeof(V4));
     uint64_t* empty_bar = full_bar + STAGES;
+    double* ssum = reinterpret_cast<double*>(empty_bar + STAGES);   // [3][R][THREADS], SS only
+    (void)ssum;
     __shared__ int s_last;
 
     const int tid = threadIdx.x;
@@ -229,7 +252,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
     }
 
     // per-thread i-body state
-    REAL xi[R], yi[R], zi[R], mi[R];
+    REAL xi[R], yi[R], zi[R];
     double sx[R], sy[R], sz[R];
     int ib = ib0, jt = jt0;    // current flat tile
     int seg_tiles = 0;         // tiles accumulated into the current segment
@@ -244,6 +267,14 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
     auto finish_segment = [&]() {
         const long long t0 = (long long)ib * nj, t1 = t0 + nj;
         bool do_final = true;
+        if constexpr (SS) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                sx[r] = ssum[(0 * R + r) * THREADS + tid];
+                sy[r] = ssum[(1 * R + r) * THREADS + tid];
+                sz[r] = ssum[(2 * R + r) * THREADS + tid];
+            }
+        }
         if (seg_tiles != njt) {
             // split i-block: publish my partial, last arriver reduces all contributors in order
             const long long slot = 2 * (long long)blockIdx.x + (seg_index == 0 ? 0 : 1);
@@ -290,8 +321,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
             for (int r = 0; r < R; ++r) {
                 const long long il = (long long)ib * IBLK + r * THREADS + tid;
                 if (il < p.n_local) {
-                    V4 ri;
-                    ri.x = xi[r]; ri.y = yi[r]; ri.z = zi[r]; ri.w = mi[r];
+                    V4 ri = posf[p.row0 + il];   // .w = mass (positions equal xi/yi/zi)
                     finalize_body(p, il, sx[r], sy[r], sz[r], ri, REAL(0));
                 }
             }
@@ -307,8 +337,14 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
                 V4 b;
                 b.x = 0; b.y = 0; b.z = 0; b.w = 0;
                 if (il < p.n_local) b = posf[p.row0 + il];
-                xi[r] = b.x; yi[r] = b.y; zi[r] = b.z; mi[r] = b.w;
-                sx[r] = 0.0; sy[r] = 0.0; sz[r] = 0.0;
+                xi[r] = b.x; yi[r] = b.y; zi[r] = b.z;
+                if constexpr (SS) {
+                    ssum[(0 * R + r) * THREADS + tid] = 0.0;
+                    ssum[(1 * R + r) * THREADS + tid] = 0.0;
+                    ssum[(2 * R + r) * THREADS + tid] = 0.0;
+                } else {
+                    sx[r] = 0.0; sy[r] = 0.0; sz[r] = 0.0;
+                }
             }
         }
         // producer step: refill the slot freed by tile k-1 with tile k+STAGES-1
@@ -359,56 +395,56 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
                             az[q] = __ffma2_rn(dz, sc, az[q]);
                         }
                     };
-                    if constexpr (PREF) {
-                        // software-pipelined: the LDS.128s of trip t+1 are issued before the math of trip t
-                        float4 nxt[UNROLL];
-#pragma unroll
-                        for (int u = 0; u < UNROLL; ++u) nxt[u] = tile[u];
-#pragma unroll 1
-                        for (int j = 0; j < TILE; j += UNROLL) {
-                            float4 cur[UNROLL];
-#pragma unroll
-                            for (int u = 0; u < UNROLL; ++u) cur[u] = nxt[u];
-                            const int jn2 = (j + UNROLL < TILE) ? (j + UNROLL) : 0;
-#pragma unroll
-                            for (int u = 0; u < UNROLL; ++u) nxt[u] = tile[jn2 + u];
-#pragma unroll
-                            for (int u = 0; u < UNROLL; ++u) interact(cur[u]);
-                        }
-                    } else {
 #pragma unroll UNROLL
-                        for (int j = 0; j < TILE; ++j) interact(tile[j]);
-                    }
+                    for (int j = 0; j < TILE; ++j) interact(tile[j]);
                 } else {
-                    // diagonal and/or ragged tile: exclude the self pair by index, stop at n_total
-                    const long long ibase = ib_g0 + tid;
+                    // diagonal and/or ragged tile: same packed math, the self pair is taken out by index
+                    // (its dx is exactly 0, so a zero factor keeps inf*0 out) and the trip count stops at
+                    // n_total.  dj = j - (row of this thread's slot 0); slot r is the self pair at dj == r*THREADS
+                    const int dj0 = (int)(j0 - (ib_g0 + tid));
+#pragma unroll 1
                     for (int j = 0; j < jn; ++j) {
                         const float4 b = tile[j];
-                        const long long dj = (j0 + j) - ibase;
+                        const int dj = dj0 + j;
 #pragma unroll
                         for (int q = 0; q < P; ++q) {
-                            const float2 dx = make_float2(b.x - xi[2 * q], b.x - xi[2 * q + 1]);
-                            const float2 dy = make_float2(b.y - yi[2 * q], b.y - yi[2 * q + 1]);
-                            const float2 dz = make_float2(b.z - zi[2 * q], b.z - zi[2 * q + 1]);
-                            float2 d2;
-                            d2.x = fmaf(dz.x, dz.x, fmaf(dy.x, dy.x, fmaf(dx.x, dx.x, e2)));
-                            d2.y = fmaf(dz.y, dz.y, fmaf(dy.y, dy.y, fmaf(dx.y, dx.y, e2)));
+                            const float2 dx = __fadd2_rn(make_float2(b.x, b.x), make_float2(-xi[2 * q], -xi[2 * q + 1]));
+                            const float2 dy = __fadd2_rn(make_float2(b.y, b.y), make_float2(-yi[2 * q], -yi[2 * q + 1]));
+                            const float2 dz = __fadd2_rn(make_float2(b.z, b.z), make_float2(-zi[2 * q], -zi[2 * q + 1]));
+                            float2 d2 = __ffma2_rn(dx, dx, make_float2(e2, e2));
+                            d2 = __ffma2_rn(dy, dy, d2);
+                            d2 = __ffma2_rn(dz, dz, d2);
                             const float2 ri = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
-                            float2 sc = make_float2((b.w * ri.x) * (ri.x * ri.x), (b.w * ri.y) * (ri.y * ri.y));
-                            if (dj == (long long)(2 * q) * THREADS) sc.x = 0.f;
-                            if (dj == (long long)(2 * q + 1) * THREADS) sc.y = 0.f;
-                            // the self pair has dx = 0 exactly; sc = 0 keeps it out (no inf*0)
-                            ax[q].x = fmaf(dx.x, sc.x, ax[q].x); ax[q].y = fmaf(dx.y, sc.y, ax[q].y);
-                            ay[q].x = fmaf(dy.x, sc.x, ay[q].x); ay[q].y = fmaf(dy.y, sc.y, ay[q].y);
-                            az[q].x = fmaf(dz.x, sc.x, az[q].x); az[q].y = fmaf(dz.y, sc.y, az[q].y);
+                            const float2 ri2 = __fmul2_rn(ri, ri);
+                            const float2 mr = __fmul2_rn(make_float2(b.w, b.w), ri);
+                            float2 sc = __fmul2_rn(mr, ri2);
+                            if (dj == (2 * q) * THREADS) sc.x = 0.f;
+                            if (dj == (2 * q + 1) * THREADS) sc.y = 0.f;
+                            ax[q] = __ffma2_rn(dx, sc, ax[q]);
+                            ay[q] = __ffma2_rn(dy, sc, ay[q]);
+                            az[q] = __ffma2_rn(dz, sc, az[q]);
                         }
                     }
                 }
+                if constexpr (SS) {
+                    // fp64 sums live in shared memory (thread-private columns): frees 6*R registers for
+                    // the scheduler; touched once per tile
 #pragma unroll
-                for (int q = 0; q < P; ++q) {
-                    sx[2 * q] += (double)ax[q].x; sx[2 * q + 1] += (double)ax[q].y;
-                    sy[2 * q] += (double)ay[q].x; sy[2 * q + 1] += (double)ay[q].y;
-                    sz[2 * q] += (double)az[q].x; sz[2 * q + 1] += (double)az[q].y;
+                    for (int q = 0; q < P; ++q) {
+                        ssum[(0 * R + 2 * q) * THREADS + tid] += (double)ax[q].x;
+                        ssum[(0 * R + 2 * q + 1) * THREADS + tid] += (double)ax[q].y;
+                        ssum[(1 * R + 2 * q) * THREADS + tid] += (double)ay[q].x;
+                        ssum[(1 * R + 2 * q + 1) * THREADS + tid] += (double)ay[q].y;
+                        ssum[(2 * R + 2 * q) * THREADS + tid] += (double)az[q].x;
+                        ssum[(2 * R + 2 * q + 1) * THREADS + tid] += (double)az[q].y;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < P; ++q) {
+                        sx[2 * q] += (double)ax[q].x; sx[2 * q + 1] += (double)ax[q].y;
+                        sy[2 * q] += (double)ay[q].x; sy[2 * q + 1] += (double)ay[q].y;
+                        sz[2 * q] += (double)az[q].x; sz[2 * q + 1] += (double)az[q].y;
+                    }
                 }
             } else {
                 float ax[R], ay[R], az[R];
@@ -464,8 +500,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
                     for (int r = 0; r < R; ++r) {
                         const double dx = b.x - xi[r], dy = b.y - yi[r], dz = b.z - zi[r];
                         const double d2 = fma(dz, dz, fma(dy, dy, fma(dx, dx, e2)));
-                        const double ri = rsqrt(d2);
-                        const double sc = (b.w * ri) * (ri * ri);
+                        const double sc = mass_over_r3(b.w, d2);
                         sx[r] = fma(dx, sc, sx[r]);
                         sy[r] = fma(dy, sc, sy[r]);
                         sz[r] = fma(dz, sc, sz[r]);
@@ -480,8 +515,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
                     for (int r = 0; r < R; ++r) {
                         const double dx = b.x - xi[r], dy = b.y - yi[r], dz = b.z - zi[r];
                         const double d2 = fma(dz, dz, fma(dy, dy, fma(dx, dx, e2)));
-                        const double ri = rsqrt(d2);
-                        double sc = (b.w * ri) * (ri * ri);
+                        double sc = mass_over_r3(b.w, d2);
                         if (dj == (long long)r * THREADS) sc = 0.0;
                         sx[r] = fma(dx, sc, sx[r]);
                         sy[r] = fma(dy, sc, sy[r]);
@@ -510,9 +544,42 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
     }
 }
 
-template <typename REAL, int THREADS, int R, int TILE, int STAGES>
+template <typename REAL, int THREADS, int R, int TILE, int STAGES, int SS>
 constexpr size_t sweep_smem_bytes() {
-    return (size_t)STAGES * TILE * sizeof(typename Vec4<REAL>::type) + 2 * STAGES * sizeof(uint64_t);
+    return (size_t)STAGES * TILE * sizeof(typename Vec4<REAL>::type) + 2 * STAGES * sizeof(uint64_t) +
+           (SS ? (size_t)3 * R * THREADS * sizeof(double) : 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross-GPU step barrier of the peer-store exchange.  Runs on the sweep's stream right after it, so all
+// of this GPU's peer stores are ordered before the flag release.  Lane q tells peer q "rank `rank` has
+// finished step `step`" (release, system scope) and then waits until peer q has said the same here.
+// One barrier per step covers both hazards: new positions have landed (RAW) and nobody still reads the
+// buffer that the next step will overwrite (WAR).  A clock-based timeout turns a dead peer into an
+// error flag instead of a hang.
+// ------------------------------------------------------------------------------------------------
+struct BarrierParams {
+    unsigned long long* my_flags;                 // [world] written by the peers
+    unsigned long long* peer_flags[kMaxPeers + 1];   // [world] each rank's flag array (entry `rank` unused)
+    int rank, world;
+    unsigned long long step;
+    unsigned long long timeout_ns;
+    int* error;                                   // set to 1 on timeout
+};
+
+__global__ void exchange_barrier_kernel(const BarrierParams b) {
+    const int q = threadIdx.x;
+    if (q >= b.world || q == b.rank) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(b.peer_flags[q] + b.rank), "l"(b.step) : "memory");
+    unsigned long long t0, t1, seen;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(b.my_flags + q) : "memory");
+        if (seen >= b.step) return;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < b.timeout_ns);
+    *b.error = 1;
 }
 
 }  // namespace gravb200

@@ -31,6 +31,7 @@ __authors__ = [
 	'gravitation_b200 authors',
 	]
 
+import os
 import threading
 
 import numpy as np
@@ -194,10 +195,14 @@ class universe(universe_base):
 	def _make_shards(self, n):
 		meta = self._meta
 		if 'world' in meta: # one process per GPU (torchrun): this process owns shard `rank`
-			return [_shim.Shard(
+			shard = _shim.Shard(
 				n, self.DTYPE, device = int(meta.get('device', 0)),
 				rank = int(meta['rank']), world = int(meta['world']), nccl_id = meta.get('nccl_id'),
-				)]
+				)
+			if int(meta['world']) > 1:
+				from ..dist import connect_peers
+				connect_peers(shard)
+			return [shard]
 		gpus = int(self._threads)
 		if gpus < 1:
 			raise ValueError('threads (= number of GPUs) must be >= 1')
@@ -221,6 +226,19 @@ class universe(universe_base):
 			w.join()
 		if errors:
 			raise errors[0]
+		# fused exchange: every shard maps every other shard's position buffers (direct peer access) and
+		# the sweep's epilogue stores r' there; all-or-nothing, NCCL all-gather otherwise
+		mode = _shim.XCHG_NCCL
+		if str(meta.get('exchange', os.environ.get('GRAVB200_EXCHANGE', 'peer'))).lower() != 'nccl':
+			try:
+				blobs = [sh.peer_export() for sh in shards]
+				for sh in shards:
+					sh.peer_connect(blobs)
+				mode = _shim.XCHG_PEER
+			except _shim.GravB200Error:
+				mode = _shim.XCHG_NCCL
+		for sh in shards:
+			sh.set_exchange_mode(mode)
 		return shards
 
 	def step_stage1(self):
@@ -233,10 +251,14 @@ class universe(universe_base):
 
 	def _commit(self):
 		if len(self._shards) > 1:
-			_shim.group_begin()
+			# enqueue the exchange on EVERY shard before waiting on any (one host thread drives them all)
+			nccl = self._shards[0].info()['exchange_mode'] == _shim.XCHG_NCCL
+			if nccl:
+				_shim.group_begin()
 			for sh in self._shards:
 				sh.exchange()
-			_shim.group_end()
+			if nccl:
+				_shim.group_end()
 		for sh in self._shards:
 			sh.stage2()
 

@@ -34,6 +34,9 @@ extern "C" {
 #define GRAVB200_ENODEV (-4)  /* no CUDA device */
 
 #define GRAVB200_NCCL_ID_BYTES 128
+#define GRAVB200_PEER_BLOB_BYTES 256
+#define GRAVB200_XCHG_NCCL 0 /* per-step in-place ncclAllGather of the new positions */
+#define GRAVB200_XCHG_PEER 1 /* fused: the sweep's epilogue stores r' into every peer over NVLink + flag barrier */
 
 typedef struct gravb200_ctx gravb200_ctx;
 
@@ -74,6 +77,16 @@ int gravb200_stage2(gravb200_ctx* ctx);
 int gravb200_exchange(gravb200_ctx* ctx);
 int gravb200_group_begin(void);
 int gravb200_group_end(void);
+
+/* Fused position exchange (replaces the NCCL all-gather; no reference counterpart).
+ * Each shard publishes a blob (GRAVB200_PEER_BLOB_BYTES: process id, device, raw pointers and CUDA IPC
+ * handles of its two position buffers and its flag array); the caller gathers the blobs of all `world`
+ * shards in rank order and hands them to every shard.  Shards of the same process use direct peer
+ * access, shards of other processes CUDA IPC.  Call before gravb200_upload.  The mode must be the same
+ * on all shards: switch only after every shard connected successfully. */
+int gravb200_peer_export(gravb200_ctx* ctx, void* blob);
+int gravb200_peer_connect(gravb200_ctx* ctx, const void* blobs);
+int gravb200_set_exchange_mode(gravb200_ctx* ctx, int mode);
 /* k fused steps without host involvement (launch-bound small N: captured in a CUDA graph). */
 int gravb200_steps(gravb200_ctx* ctx, int k);
 int gravb200_sync(gravb200_ctx* ctx);
@@ -91,7 +104,8 @@ int gravb200_timings(gravb200_ctx* ctx, float* ms, int n);
 
 /* Introspection used by bench.py / tests: launch geometry and counters.
  * info[0]=grid, [1]=threads, [2]=i-bodies per thread, [3]=j tile, [4]=stages, [5]=dynamic smem bytes,
- * [6]=kernel launches so far, [7]=SM count, [8]=packed f32x2 (1/0), [9]=resident CTAs per SM. */
+ * [6]=kernel launches so far, [7]=SM count, [8]=packed f32x2 (1/0), [9]=resident CTAs per SM,
+ * [10]=exchange mode (GRAVB200_XCHG_*). */
 int gravb200_info(const gravb200_ctx* ctx, int64_t* info, int n);
 /* Force a kernel variant (tests / ncu A-B): variant < 0 restores the automatic choice. */
 int gravb200_set_variant(gravb200_ctx* ctx, int variant);

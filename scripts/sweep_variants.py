@@ -64,7 +64,7 @@ def time_variant(sh, reps):
     time_variant.mhz = t['sm_mhz']
     return best
 
-for dtype, sizes in (('float32', [262144]), ('float64', [65536])):
+for dtype, sizes in (('float32', [65536]), ('float64', [65536, 262144])):
     names = _shim.variant_names(dtype)
     results = {}
     for n in sizes:
@@ -81,7 +81,7 @@ for dtype, sizes in (('float32', [262144]), ('float64', [65536])):
         sh.close()
     if dtype == 'float32' and not quick:
         n = 1 << 20
-        top = sorted(range(len(names)), key=lambda vi: -results[(262144, vi)])[:4]
+        top = [0]
         r, v, m = universe(n, 13, dtype)
         sh = _shim.Shard(n, dtype)
         sh.upload(r, v, m, G, T)

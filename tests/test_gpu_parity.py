@@ -305,3 +305,70 @@ def test_multi_gpu_in_one_process_matches_single_gpu(oracle, gpu):
 	assert traj_err(states[1][1], states[0][1].astype(np.float64)) <= 1e-6
 	r4_ref, _ = oracle.steps(r, v, m, G, T, 4)
 	assert traj_err(states[1][0], r4_ref) <= 5e-6
+
+
+def test_peer_store_exchange_equals_nccl_exchange_bitwise(oracle, gpu):
+	"""fused exchange (epilogue stores r' into the peers over NVLink + flag barrier) vs the NCCL
+	all-gather: same kernel, same shards, so the trajectories must be bit-identical"""
+	if gpu.device_count() < 2:
+		pytest.skip('needs 2 GPUs')
+	from gravitation_b200.kernel import b200
+	n = 20011
+	r, v, m, G, T = oracle.uniform_universe(n, 6, 'float64')
+	out = {}
+	for exchange in ('nccl', 'peer'):
+		u = b200.universe(T = T, G = G, scale_off = True, dtype = 'float32', threads = 2, exchange = exchange)
+		u.add_objects(r, v, m, scale_off = True)
+		u.start()
+		assert u._shards[0].info()['exchange_mode'] == (gpu.XCHG_PEER if exchange == 'peer' else gpu.XCHG_NCCL)
+		for _ in range(3):
+			u.step()
+		u.steps(3)
+		out[exchange] = (np.array([pm._r for pm in u]), np.array([pm._v for pm in u]))
+		u.stop()
+	assert np.array_equal(out['nccl'][0], out['peer'][0]) and np.array_equal(out['nccl'][1], out['peer'][1])
+	r6_ref, _ = oracle.steps(r, v, m, G, T, 6)
+	assert traj_err(out['peer'][0], r6_ref) <= 5e-6
+
+
+def _rank_worker(rank, world, port, n, out_dir):
+	import os
+	os.environ.update(RANK = str(rank), WORLD_SIZE = str(world), LOCAL_RANK = str(rank),
+		MASTER_ADDR = '127.0.0.1', MASTER_PORT = str(port))
+	import torch.distributed as tdist
+	from gravitation_b200 import dist
+	from oracle import oracle
+	dist.init_process_group(backend = 'gloo') # rendezvous on CPU; the data path is the library's own
+	r, v, m, G, T = oracle.uniform_universe(n, 8, 'float32')
+	shard = dist.make_shard(n, 'float32') # CUDA IPC peer-store exchange when possible, else NCCL
+	shard.upload(r, v, m, G, T)
+	shard.steps(2)
+	for _ in range(2):
+		shard.stage1(); shard.stage2()
+	rr, vv, aa = shard.download(a = True)
+	v_full = dist.gather_rows(vv, n)
+	np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), r = rr, v = v_full, mode = shard.info()['exchange_mode'])
+	shard.close()
+	tdist.destroy_process_group()
+
+
+def test_one_process_per_gpu_matches_single_gpu(oracle, gpu, tmp_path):
+	"""the torchrun launch model: 2 processes, 2 GPUs, row-sharded, fused exchange over CUDA IPC"""
+	if gpu.device_count() < 2:
+		pytest.skip('needs 2 GPUs')
+	import socket
+	import torch.multiprocessing as mp
+	n = 30011
+	s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+	mp.spawn(_rank_worker, args = (2, port, n, str(tmp_path)), nprocs = 2, join = True)
+	r, v, m, G, T = oracle.uniform_universe(n, 8, 'float32')
+	sh = gpu.Shard(n, 'float32')
+	sh.upload(r, v, m, G, T)
+	sh.steps(4)
+	r1, v1, _ = sh.download()
+	sh.close()
+	for rank in range(2):
+		with np.load(str(tmp_path / ('rank%d.npz' % rank))) as f:
+			assert traj_err(f['r'], r1.astype(np.float64)) <= 1e-6
+			assert traj_err(f['v'], v1.astype(np.float64)) <= 1e-6
+			assert int(f['mode']) in (gpu.XCHG_PEER, gpu.XCHG_NCCL)
