@@ -294,7 +294,7 @@ def own_arm(args):
 		'dtype': args.dtype, 'data': 'synthetic',
 		'config': {
 			'workload': 'all-pairs step (stage 1 sweep + fused stage 2), uniform universe, N=2^%d %s' % (args.bodies, args.dtype),
-			'n_bodies': n, 'parallelism': 'row-sharded x%d, NCCL all-gather of positions' % world if world > 1 else 'single GPU',
+			'n_bodies': n, 'parallelism': ('row-sharded x%d, %s' % (world, 'fused peer-store exchange over NVLink (CUDA IPC) + flag barrier' if info['exchange_mode'] == 1 else 'NCCL all-gather of positions')) if world > 1 else 'single GPU',
 			'grid': info['grid'], 'threads': info['threads'], 'bodies_per_thread': info['bodies_per_thread'], 'tile': info['tile'],
 			'l2': 'flushed between timed steps (256 MiB write); the 16 MiB position array is then re-read from L2 by design',
 			},
@@ -316,6 +316,15 @@ def own_arm(args):
 	return 0
 
 
+def _shutdown():
+	try:
+		import torch.distributed as tdist
+		if tdist.is_initialized():
+			tdist.destroy_process_group()
+	except Exception:
+		pass
+
+
 def main():
 	ap = argparse.ArgumentParser()
 	ap.add_argument('--gpus', type = int, default = 1)
@@ -330,7 +339,9 @@ def main():
 		args.warmup = 3
 	if args.impl == 'reference':
 		return reference_arm(args)
-	return own_arm(args)
+	rc = own_arm(args)
+	_shutdown()
+	return rc
 
 
 if __name__ == '__main__':

@@ -124,11 +124,11 @@ Variant make_variant(const char* name) {
 
 const std::vector<Variant>& variants_f32() {
     static const std::vector<Variant> v = {
-        V32(256, 8, 512, 3, 1, 1, 2, 0),    // 0  auto: large N   (IBLK 2048)
+        V32(256, 8, 512, 3, 1, 1, 4, 1),    // 0  auto: large N   (IBLK 2048), fp64 sums in shared memory
         V32(256, 4, 256, 3, 2, 1, 2, 0),    // 1  auto            (IBLK 1024)
         V32(128, 4, 128, 3, 4, 1, 2, 0),    // 2  auto            (IBLK 512)
         V32(128, 2, 64, 4, 4, 1, 2, 0),     // 3  auto: tiny N    (IBLK 256)
-        V32(256, 8, 512, 3, 1, 0, 2, 0),    // 4  scalar-FFMA twin of 0 (A/B evidence)
+        V32(256, 8, 512, 3, 1, 0, 2, 0),    // 4  scalar-FFMA twin of 13 (A/B evidence)
         V32(512, 4, 512, 3, 1, 1, 2, 0),    // 5
         V32(256, 8, 512, 3, 1, 1, 2, 1),    // 6  0 with shared-memory sums
         V32(384, 8, 512, 3, 1, 1, 2, 1),    // 7
@@ -137,7 +137,7 @@ const std::vector<Variant>& variants_f32() {
         V32(384, 8, 512, 3, 1, 1, 1, 1),    // 10
         V32(512, 6, 512, 3, 1, 1, 2, 1),    // 11
         V32(512, 4, 512, 3, 1, 1, 2, 1),    // 12
-        V32(256, 8, 512, 3, 1, 1, 4, 1),    // 13
+        V32(256, 8, 512, 3, 1, 1, 2, 0),    // 13 register-resident sums, unroll 2 (the round-1 default)
         V32(384, 6, 512, 3, 1, 1, 2, 1),    // 14
         V32(256, 12, 512, 3, 1, 1, 2, 1),   // 15
         V32(256, 8, 512, 3, 2, 1, 2, 1),    // 16
@@ -644,8 +644,10 @@ int gravb200_upload(gravb200_ctx* c, const void* r, const void* v, const void* m
                        cudaMemcpyDeviceToDevice, c->stream));
     // peer-store mode: nobody may start writing r' into this GPU's back buffer before the copy above
     // is done everywhere (every rank calls upload, so the barrier generations stay in lockstep)
-    if (c->peer_mode) { rc = peer_barrier(c); if (rc) return rc; }
+    // The barrier is only ENQUEUED (the first sweep is stream-ordered behind it): a host thread that
+    // drives several shards uploads them one after the other and must not block here.
     CU(cudaStreamSynchronize(c->stream));
+    if (c->peer_mode) { rc = peer_barrier(c); if (rc) return rc; }
     c->uploaded = true;
     return 0;
 }

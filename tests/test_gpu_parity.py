@@ -372,3 +372,18 @@ def test_one_process_per_gpu_matches_single_gpu(oracle, gpu, tmp_path):
 			assert traj_err(f['r'], r1.astype(np.float64)) <= 1e-6
 			assert traj_err(f['v'], v1.astype(np.float64)) <= 1e-6
 			assert int(f['mode']) in (gpu.XCHG_PEER, gpu.XCHG_NCCL)
+
+
+def test_worker_log_round_trips_through_analyze(gpu, tmp_path):
+	"""cli plumbing on the real kernel: worker subprocess -> JSON-lines log -> analyze"""
+	import json, os, subprocess, sys
+	from gravitation_b200.cli import analyze
+	root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+	cmd = [sys.executable, '-m', 'gravitation_b200.cli.worker', '-k', 'b200', '--scenario_param',
+		json.dumps({'stars_len': 2048, 'seed': 3}), '-i', '4', '-t', '0', '-s', '2', '-o', str(tmp_path / 'data.h5')]
+	out = subprocess.run(cmd, cwd = root, capture_output = True, text = True, timeout = 300)
+	assert out.returncode == 0, out.stderr[-2000:]
+	runs = analyze.parse_log(out.stdout)
+	assert len(runs) == 1 and len(runs[0]['runtime']) == 4 and runs[0]['meta']['simulation']['size'] == 2048
+	assert all(t > 0 for t in runs[0]['runtime'])
+	assert any(fn.startswith('data.h5') for fn in os.listdir(str(tmp_path))) # --save_after_iteration 2 wrote a snapshot

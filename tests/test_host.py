@@ -194,3 +194,41 @@ def test_row_partition_covers_all_rows():
 			if cnt:
 				assert row0 == pos
 			pos += cnt
+
+
+# ---- worker protocol / analyze (cli/worker.py:115-245, cli/analyze.py:47-108) ----------------------
+
+def _fake_log(steps = 3, exit_ok = True, extra = ''):
+	import json
+	lines = ['{"log": "START"}', json.dumps({'log': 'INPUT', 'simulation': {'kernel': 'b200', 'threads': 1}}),
+		json.dumps({'log': 'PROCEDURE', 'msg': 'x'}), json.dumps({'log': 'SIZE', 'value': 16})]
+	for k in range(1, steps + 1):
+		lines += [json.dumps({'log': 'STEP', 'runtime': 100 + k, 'gctime': 5, 'counter': k}), json.dumps({'log': 'BEST_TIME', 'value': 101})]
+	lines += [json.dumps({'log': 'RATE', 'best_interactions_per_s': 1.0})] # our extra line type is ignored
+	if extra:
+		lines.append(extra)
+	if exit_ok:
+		lines.append(json.dumps({'log': 'EXIT', 'msg': 'OK'}))
+	return '\n'.join(lines) + '\n'
+
+
+def test_analyze_accepts_good_logs_and_rejects_bad_ones():
+	from gravitation_b200.cli import analyze
+	runs = analyze.parse_log(_fake_log() + _fake_log(steps = 2))
+	assert len(runs) == 2 and runs[0]['runtime'] == [101, 102, 103] and runs[0]['meta']['simulation']['size'] == 16
+	for bad, msg in (
+		(_fake_log(exit_ok = False), 'did not exit properly'),
+		(_fake_log(extra = 'not json'), 'non-JSON'),
+		(_fake_log(extra = '{"log": "ERROR", "msg": "boom"}'), 'has errors'),
+		(_fake_log(steps = 0), 'did not run any steps'),
+		(_fake_log().replace('"counter": 2', '"counter": 7'), 'unexpected sequence'),
+		):
+		with pytest.raises(SyntaxError, match = msg):
+			analyze.parse_log(bad)
+
+
+def test_benchmark_size_range_matches_reference_rule():
+	from gravitation_b200.cli.benchmark import size_range, worker_command
+	assert size_range(2, 4) == [4, 6, 8, 12, 16] and size_range(3, 3) == [8]
+	cmd = worker_command('b200', 4096, 2, 10, 0)
+	assert cmd[1:3] == ['-m', 'gravitation_b200.cli.worker'] and '{"stars_len": 4096}' in cmd and cmd[-1] == '2'
