@@ -70,6 +70,25 @@ class GravB200Error(RuntimeError):
 	"""a libgravb200 call returned a negative status"""
 
 
+def _prefer_bundled_nccl():
+	"""libgravb200 dlopens NCCL by soname when a multi-GPU context is created.  If that happened before
+	`import torch`, the system libnccl.so.2 would win and torch (which needs the newer NCCL bundled in
+	its wheel) could no longer be imported into the process.  Point the library at the bundled copy when
+	there is one; GRAVB200_NCCL_LIB set by the user is respected."""
+	if os.environ.get('GRAVB200_NCCL_LIB'):
+		return
+	try:
+		import importlib.util
+		spec = importlib.util.find_spec('nvidia.nccl')
+		for loc in (spec.submodule_search_locations if spec is not None else []):
+			cand = os.path.join(loc, 'lib', 'libnccl.so.2')
+			if os.path.isfile(cand):
+				os.environ['GRAVB200_NCCL_LIB'] = cand
+				return
+	except Exception:
+		pass
+
+
 def load():
 	"""dlopen libgravb200.so and declare every prototype; raises if the library was not built"""
 	global _lib
@@ -80,6 +99,7 @@ def load():
 			'%s not found: build it with `make -C gravitation_b200/csrc` '
 			'(or `python -c "import __graft_entry__ as g; g.build()"`). There is no CPU fallback.' % LIB_PATH
 			)
+	_prefer_bundled_nccl()
 	lib = ctypes.CDLL(LIB_PATH, mode = ctypes.RTLD_GLOBAL)
 	for name, restype, argtypes in _SIGNATURES:
 		fn = getattr(lib, name) # AttributeError if the symbol is missing
