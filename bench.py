@@ -285,6 +285,16 @@ def own_arm(args):
 		except Exception as e:
 			cpu = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'reference', 'sample': 'failed: %s' % str(e)[:200]}
 
+	# ---- the reference's own GPU kernel (pc2) on this B200: reported baseline, N = 1 only ------------
+	gpu_ref = None
+	if world == 1 and not args.no_cpu_baseline and dtype == 'float32':
+		try:
+			from oracle import pc2_bench
+			if pc2_bench.available(n, dtype):
+				gpu_ref = pc2_bench.run(args.bodies, steps = 2, warmup = 1, dtype = dtype)
+		except Exception as e:
+			gpu_ref = {'error': str(e)[:300]}
+
 	line = {
 		'metric': METRIC if (args.bodies == 20 and dtype == 'float32') else 'G body-interactions/s at N=2^%d %s' % (args.bodies, args.dtype),
 		'value': value, 'unit': UNIT,
@@ -312,6 +322,8 @@ def own_arm(args):
 		}
 	if cpu is not None:
 		line['cpu_baseline'] = cpu
+	if gpu_ref is not None:
+		line['reference_gpu_kernel'] = gpu_ref
 	print(json.dumps(line), flush = True)
 	return 0
 
