@@ -215,9 +215,10 @@ def own_arm(args):
 	def e2e_step():
 		u.push_host_state()   # H2D of the step's inputs from the pinned host mirrors
 		u.step()              # stage 1 (+ D2H of a), stage 2 (+ D2H of r, v), eager_host = True
-	for _ in range(min(args.warmup, 3)):
+	e2e_warm = 1 if args.quick_e2e else min(args.warmup, 3)
+	for _ in range(e2e_warm):
 		e2e_step()
-	e2e_steps = max(3, min(args.steps, 5))
+	e2e_steps = 1 if args.quick_e2e else max(3, min(args.steps, 5))
 	torch.cuda.synchronize(); dist.barrier() if world > 1 else None
 	t0 = time.perf_counter()
 	for _ in range(e2e_steps):
@@ -346,6 +347,7 @@ def main():
 	ap.add_argument('--bodies', type = int, default = 20, help = 'log2 of the number of bodies (default: the north-star 2^20)')
 	ap.add_argument('--dtype', default = 'f32', choices = ('f32', 'f64'))
 	ap.add_argument('--no-cpu-baseline', action = 'store_true')
+	ap.add_argument('--quick-e2e', action = 'store_true', help = 'one warm-up + one timed end-to-end step (very large N)')
 	args = ap.parse_args()
 	if args.warmup < 3:
 		args.warmup = 3
