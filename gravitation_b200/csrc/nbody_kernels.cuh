@@ -27,6 +27,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace gravb200 {
 
 constexpr int kMaxPeers = 15;   // one 16-GPU NVSwitch domain at most
@@ -376,54 +378,48 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
 #pragma unroll
                 for (int q = 0; q < P; ++q) ax[q] = ay[q] = az[q] = make_float2(0.f, 0.f);
                 const float e2 = p.eps2_f;
-                if (!special) {
-                    auto interact = [&](const float4 b) {
+                // one interaction of the j-body b with every i-pair of this thread.  MASKED: the self pair is
+                // taken out by index — dj = j - (row of this thread's slot 0), slot r is the self pair at
+                // dj == r*THREADS; its dx is exactly 0, so a zero factor keeps inf*0 out.  The compares and
+                // selects go to the ALU pipe, whose issue slots are idle here.
+                auto interact = [&](const float4 b, auto masked, const int dj) {
 #pragma unroll
-                        for (int q = 0; q < P; ++q) {
-                            const float2 dx = __fadd2_rn(make_float2(b.x, b.x), make_float2(-xi[2 * q], -xi[2 * q + 1]));
-                            const float2 dy = __fadd2_rn(make_float2(b.y, b.y), make_float2(-yi[2 * q], -yi[2 * q + 1]));
-                            const float2 dz = __fadd2_rn(make_float2(b.z, b.z), make_float2(-zi[2 * q], -zi[2 * q + 1]));
-                            float2 d2 = __ffma2_rn(dx, dx, make_float2(e2, e2));
-                            d2 = __ffma2_rn(dy, dy, d2);
-                            d2 = __ffma2_rn(dz, dz, d2);
-                            const float2 ri = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
-                            const float2 ri2 = __fmul2_rn(ri, ri);
-                            const float2 mr = __fmul2_rn(make_float2(b.w, b.w), ri);
-                            const float2 sc = __fmul2_rn(mr, ri2);
-                            ax[q] = __ffma2_rn(dx, sc, ax[q]);
-                            ay[q] = __ffma2_rn(dy, sc, ay[q]);
-                            az[q] = __ffma2_rn(dz, sc, az[q]);
-                        }
-                    };
-#pragma unroll UNROLL
-                    for (int j = 0; j < TILE; ++j) interact(tile[j]);
-                } else {
-                    // diagonal and/or ragged tile: same packed math, the self pair is taken out by index
-                    // (its dx is exactly 0, so a zero factor keeps inf*0 out) and the trip count stops at
-                    // n_total.  dj = j - (row of this thread's slot 0); slot r is the self pair at dj == r*THREADS
-                    const int dj0 = (int)(j0 - (ib_g0 + tid));
-#pragma unroll 1
-                    for (int j = 0; j < jn; ++j) {
-                        const float4 b = tile[j];
-                        const int dj = dj0 + j;
-#pragma unroll
-                        for (int q = 0; q < P; ++q) {
-                            const float2 dx = __fadd2_rn(make_float2(b.x, b.x), make_float2(-xi[2 * q], -xi[2 * q + 1]));
-                            const float2 dy = __fadd2_rn(make_float2(b.y, b.y), make_float2(-yi[2 * q], -yi[2 * q + 1]));
-                            const float2 dz = __fadd2_rn(make_float2(b.z, b.z), make_float2(-zi[2 * q], -zi[2 * q + 1]));
-                            float2 d2 = __ffma2_rn(dx, dx, make_float2(e2, e2));
-                            d2 = __ffma2_rn(dy, dy, d2);
-                            d2 = __ffma2_rn(dz, dz, d2);
-                            const float2 ri = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
-                            const float2 ri2 = __fmul2_rn(ri, ri);
-                            const float2 mr = __fmul2_rn(make_float2(b.w, b.w), ri);
-                            float2 sc = __fmul2_rn(mr, ri2);
+                    for (int q = 0; q < P; ++q) {
+                        const float2 dx = __fadd2_rn(make_float2(b.x, b.x), make_float2(-xi[2 * q], -xi[2 * q + 1]));
+                        const float2 dy = __fadd2_rn(make_float2(b.y, b.y), make_float2(-yi[2 * q], -yi[2 * q + 1]));
+                        const float2 dz = __fadd2_rn(make_float2(b.z, b.z), make_float2(-zi[2 * q], -zi[2 * q + 1]));
+                        float2 d2 = __ffma2_rn(dx, dx, make_float2(e2, e2));
+                        d2 = __ffma2_rn(dy, dy, d2);
+                        d2 = __ffma2_rn(dz, dz, d2);
+                        const float2 ri = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
+                        const float2 ri2 = __fmul2_rn(ri, ri);
+                        const float2 mr = __fmul2_rn(make_float2(b.w, b.w), ri);
+                        float2 sc = __fmul2_rn(mr, ri2);
+                        if constexpr (decltype(masked)::value) {
                             if (dj == (2 * q) * THREADS) sc.x = 0.f;
                             if (dj == (2 * q + 1) * THREADS) sc.y = 0.f;
-                            ax[q] = __ffma2_rn(dx, sc, ax[q]);
-                            ay[q] = __ffma2_rn(dy, sc, ay[q]);
-                            az[q] = __ffma2_rn(dz, sc, az[q]);
                         }
+                        ax[q] = __ffma2_rn(dx, sc, ax[q]);
+                        ay[q] = __ffma2_rn(dy, sc, ay[q]);
+                        az[q] = __ffma2_rn(dz, sc, az[q]);
+                    }
+                };
+                using yes = std::true_type;
+                using no = std::false_type;
+                if (!special) {
+#pragma unroll UNROLL
+                    for (int j = 0; j < TILE; ++j) interact(tile[j], no{}, 0);
+                } else {
+                    const int dj0 = (int)(j0 - (ib_g0 + tid));
+                    if (jn == TILE) {
+                        // diagonal tile: full trip count, unrolled like the fast loop (these tiles cluster in a
+                        // few CTAs, so their speed decides the kernel's tail at small N)
+#pragma unroll UNROLL
+                        for (int j = 0; j < TILE; ++j) interact(tile[j], yes{}, dj0 + j);
+                    } else {
+                        // ragged last tile: stop at n_total
+#pragma unroll 1
+                        for (int j = 0; j < jn; ++j) interact(tile[j], yes{}, dj0 + j);
                     }
                 }
                 if constexpr (SS) {
