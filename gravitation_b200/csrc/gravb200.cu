@@ -249,6 +249,17 @@ long long tiles_of(const gravb200_ctx* c, const Variant& v) {
     return nib * njt;
 }
 
+// CTAs to launch for `tiles` flat tiles on `slots` resident CTA slots: all slots when there is enough
+// work, otherwise few enough CTAs that each still gets >= 4 tiles (fewer contributors per split
+// i-block, less fixed cost per unit of work)
+long long grid_for(long long tiles, long long slots) {
+    long long g = slots;
+    if (tiles < 4 * slots) g = std::max<long long>(1, tiles / 4);
+    if (g > slots) g = slots;
+    if (g > tiles) g = tiles;
+    return std::max<long long>(g, 1);
+}
+
 // choose the variant and size its workspace
 int pick_variant(gravb200_ctx* c) {
     const auto& vs = variants_of(c->dtype);
@@ -259,18 +270,35 @@ int pick_variant(gravb200_ctx* c) {
         int rc = occupancy_of(vs[pick], &occ);
         if (rc) return rc;
     } else {
+        // Cost model (relative units): a CTA gets 1/occ of its SM, tiles run at the variant's measured
+        // inner-loop speed (profiles/r01_sweep*_variants.jsonl, large N), the slowest CTA runs
+        // ceil(tiles / grid) tiles, and every launch pays a fixed cost plus one fix-up term per
+        // contributor of a split i-block.  Small N thereby moves to finer-grained variants by itself.
+        static const double kSpeed32[kAutoF32] = {1.00, 0.90, 0.87, 0.76};
+        static const double kSpeed64[kAutoF64] = {1.00, 0.95, 0.85};
+        double best_cost = 0;
         for (int i = 0; i < n_auto; ++i) {
-            int rc = occupancy_of(vs[i], &occ);
+            int o = 0;
+            int rc = occupancy_of(vs[i], &o);
             if (rc) return rc;
-            if (tiles_of(c, vs[i]) >= 8LL * occ * c->sm_count) { pick = i; break; }
+            const double speed = c->dtype == GRAVB200_F32 ? kSpeed32[i] : kSpeed64[i];
+            const long long tiles = tiles_of(c, vs[i]);
+            if (tiles <= 0) continue;
+            const long long g = grid_for(tiles, (long long)o * c->sm_count);
+            const double per_tile = (double)vs[i].threads * vs[i].r * vs[i].tile * o / speed;   // SM-share units
+            const double rounds = (double)((tiles + g - 1) / g);
+            const double njt = (double)((c->n_total + vs[i].tile - 1) / vs[i].tile);
+            const double contributors = std::max(1.0, njt / std::max(1.0, (double)tiles / (double)g));
+            const double fixed = 150000.0 + 6000.0 * contributors;   // ~8 us launch/prologue + ~0.3 us per contributor
+            const double cost = rounds * per_tile + fixed;
+            if (i == 0 || cost < best_cost) { best_cost = cost; pick = i; }
         }
         int rc = occupancy_of(vs[pick], &occ);
         if (rc) return rc;
     }
     const Variant& v = vs[pick];
     const long long total = tiles_of(c, v);
-    long long grid = (long long)occ * c->sm_count;
-    if (grid > total) grid = total;
+    long long grid = grid_for(total, (long long)occ * c->sm_count);
     c->variant = pick;
     c->occ = occ;
     c->grid = (int)grid;

@@ -123,6 +123,12 @@ __device__ __forceinline__ double ld_cg_f64(const double* p) {
     return v;
 }
 
+__device__ __forceinline__ double4 ld_cg_d4(const double4* p) {   // L2-coherent 32-byte load
+    const double2 a = __ldcg(reinterpret_cast<const double2*>(p));
+    const double2 b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
 // stream-K partition helpers: CTA c owns flat tiles [lo(c), lo(c+1))
 __device__ __forceinline__ long long sk_lo(long long total, long long c, long long S) {
     return total * c / S;
@@ -302,18 +308,25 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
                 const long long c_first = sk_owner(total, t0, S), c_last = sk_owner(total, t1 - 1, S);
 #pragma unroll
                 for (int r = 0; r < R; ++r) { sx[r] = 0.0; sy[r] = 0.0; sz[r] = 0.0; }
+                // contributors in CTA order (fixed order = deterministic sum).  lo(c) is carried from one
+                // contributor to the next (one division each), in 32 bits when the products fit.
+                const bool small = (unsigned long long)total * (unsigned long long)(S + 1) < 0xffffffffull;
+                auto lo_of = [&](long long c) -> long long {
+                    return small ? (long long)((unsigned int)total * (unsigned int)c / (unsigned int)S) : sk_lo(total, c, S);
+                };
+                long long clo = lo_of(c_first);
                 for (long long c = c_first; c <= c_last; ++c) {
-                    const long long clo = sk_lo(total, c, S), chi = sk_lo(total, c + 1, S);
-                    if (clo >= chi) continue;
+                    const long long chi = lo_of(c + 1);
+                    const bool empty = clo >= chi;
                     const long long cs = 2 * c + ((clo >= t0) ? 0 : 1);
-                    const double* src = p.partial + cs * (long long)IBLK * 4;
+                    clo = chi;
+                    if (empty) continue;
+                    const double4* src = reinterpret_cast<const double4*>(p.partial + cs * (long long)IBLK * 4);
+                    double4 part[R];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const double* q = src + (size_t)(r * THREADS + tid) * 4;
-                        sx[r] += ld_cg_f64(q + 0);
-                        sy[r] += ld_cg_f64(q + 1);
-                        sz[r] += ld_cg_f64(q + 2);
-                    }
+                    for (int r = 0; r < R; ++r) part[r] = ld_cg_d4(src + r * THREADS + tid);   // all loads in flight first
+#pragma unroll
+                    for (int r = 0; r < R; ++r) { sx[r] += part[r].x; sy[r] += part[r].y; sz[r] += part[r].z; }
                 }
             }
             __syncthreads();   // s_last may be rewritten by the next segment

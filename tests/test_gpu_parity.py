@@ -391,3 +391,11 @@ def test_worker_log_round_trips_through_analyze(gpu, tmp_path):
 	assert len(runs) == 1 and len(runs[0]['runtime']) == 4 and runs[0]['meta']['simulation']['size'] == 2048
 	assert all(t > 0 for t in runs[0]['runtime'])
 	assert any(fn.startswith('data.h5') for fn in os.listdir(str(tmp_path))) # --save_after_iteration 2 wrote a snapshot
+
+
+def test_accuracy_command_float32_against_float64(gpu):
+	"""`gravitation accuracy` (TODO.md:4 of the reference): same kernel, float32 vs float64, seeded galaxy"""
+	from gravitation_b200.cli import accuracy
+	out = accuracy.main(['-k', 'b200', '--dtype', 'float32', '--ref_dtype', 'float64', '-n', '1024', '-s', '5'])
+	assert out['bodies'] == 1024
+	assert out['acceleration_max_rel'] <= 1e-4 and out['position_max_rel'] <= 5e-6 and out['velocity_max_rel'] <= 5e-6
