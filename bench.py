@@ -254,12 +254,22 @@ def own_arm(args):
 			traffic = json.load(open(tpath)).get('%s_2p%d' % (args.dtype, args.bodies))
 		except Exception:
 			traffic = None
+	symmetric = info.get('variant', 0) >= _shim.SYM_BASE
+	# executed work per ORDERED interaction (the metric's unit): ordered sweep 12 FP32-pipe lane-ops = 19 FLOP,
+	# symmetric sweep (every unordered pair once, both bodies updated) 8 lane-ops = 13 FLOP; fp64 sweep 16 ops
+	lane_ops = (8.0 if symmetric else 12.0) if dtype == 'float32' else 16.0
+	flop_exec = (13.0 if symmetric else 19.0) if dtype == 'float32' else 29.0
+	pipe_ceiling = sm_count * lanes * sm_max * 1e6 / lane_ops / 1e9   # G interactions/s if the FP pipe never idled
 	roofline = {
 		'bound': 'fp32_fma' if dtype == 'float32' else 'fp64_fma',
 		'achieved': achieved, 'peak': peak_measured, 'unit': 'TFLOP/s', 'frac': achieved / peak_measured,
 		'peak_source': 'measured FFMA2/DFMA chain microbenchmark on this GPU (gravb200_peak_probe)',
 		'peak_nominal': peak_nominal, 'frac_nominal': achieved / peak_nominal,
 		'flop_per_interaction': FLOP_PER_INTERACTION,
+		'kernel': 'symmetric (Newton 3rd law, every unordered pair once)' if symmetric else 'ordered (every ordered pair)',
+		'executed_flop_per_interaction': flop_exec, 'achieved_executed': achieved * flop_exec / FLOP_PER_INTERACTION,
+		'pipe_lane_ops_per_interaction': lane_ops, 'pipe_ceiling_g_inter_s': pipe_ceiling,
+		'frac_of_pipe_ceiling': (per_gpu_rate / 1e9) / pipe_ceiling,
 		'kernel_ms': kernel_s * 1e3, 'kernel_share_of_step': float(np.sum(sweep_ms) / max(np.sum(step_ms), 1e-9)),
 		'traffic': traffic,
 		'algorithmic_hbm_bytes': int(n * 4 * esz + (n // world) * 4 * esz * 4),

@@ -16,7 +16,7 @@ import numpy as np
 
 F32, F64 = 0, 1
 NCCL_ID_BYTES = 128
-PEER_BLOB_BYTES = 256
+PEER_BLOB_BYTES = 512
 XCHG_NCCL, XCHG_PEER = 0, 1
 _DTYPES = {'float32': F32, 'float64': F64}
 
@@ -55,6 +55,7 @@ _SIGNATURES = [
 	('gravb200_info', ctypes.c_int, [_c_ctx, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
 	('gravb200_set_variant', ctypes.c_int, [_c_ctx, ctypes.c_int]),
 	('gravb200_variant_count', ctypes.c_int, [ctypes.c_int]),
+	('gravb200_sym_variant_count', ctypes.c_int, []),
 	('gravb200_variant_name', ctypes.c_char_p, [ctypes.c_int, ctypes.c_int]),
 	('gravb200_device_ptr', ctypes.c_void_p, [_c_ctx, ctypes.c_int]),
 	('gravb200_host_alloc', ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
@@ -139,10 +140,20 @@ def peak_probe(device = 0):
 	return dict(fp32_tflops = out[0], fp32x2_tflops = out[1], fp64_tflops = out[2], mufu_gops = out[3], sm_mhz = out[4])
 
 
+SYM_BASE = 100 # ids of the symmetric fp32 sweeps start here
+
+
 def variant_names(dtype = 'float32'):
+	"""ordered sweeps of `dtype` (ids 0 .. len-1)"""
 	lib = load()
 	d = _DTYPES[dtype]
 	return [lib.gravb200_variant_name(d, i).decode() for i in range(lib.gravb200_variant_count(d))]
+
+
+def sym_variant_names():
+	"""symmetric fp32 sweeps (ids SYM_BASE + k)"""
+	lib = load()
+	return [lib.gravb200_variant_name(F32, SYM_BASE + k).decode() for k in range(lib.gravb200_sym_variant_count())]
 
 
 class PinnedArray:
@@ -263,14 +274,14 @@ class Shard:
 		return (out_r if r else None, out_v if v else None, out_a if a else None)
 
 	def timings(self):
-		ms = (ctypes.c_float * 4)()
-		_check(self._lib.gravb200_timings(self._ctx, ms, 4))
-		return dict(sweep_ms = ms[0], exchange_ms = ms[1], steps_ms = ms[2], sm_mhz = ms[3])
+		ms = (ctypes.c_float * 5)()
+		_check(self._lib.gravb200_timings(self._ctx, ms, 5))
+		return dict(sweep_ms = ms[0], exchange_ms = ms[1], steps_ms = ms[2], sm_mhz = ms[3], cta0_ms = ms[4])
 
 	def info(self):
-		v = (ctypes.c_int64 * 11)()
-		_check(self._lib.gravb200_info(self._ctx, v, 11))
-		keys = ('grid', 'threads', 'bodies_per_thread', 'tile', 'stages', 'smem_bytes', 'launches', 'sm_count', 'packed', 'ctas_per_sm', 'exchange_mode')
+		v = (ctypes.c_int64 * 12)()
+		_check(self._lib.gravb200_info(self._ctx, v, 12))
+		keys = ('grid', 'threads', 'bodies_per_thread', 'tile', 'stages', 'smem_bytes', 'launches', 'sm_count', 'packed', 'ctas_per_sm', 'exchange_mode', 'variant')
 		return dict(zip(keys, [int(x) for x in v]))
 
 	def set_variant(self, variant):

@@ -11,6 +11,7 @@
 //   stop_kernel   _base_.py:174-177  -> gravb200_ctx_destroy
 #include "../../include/gravb200.h"
 #include "nbody_kernels.cuh"
+#include "nbody_sym.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -162,6 +163,45 @@ const std::vector<Variant>& variants_f64() {
 }
 constexpr int kAutoF64 = 3;
 
+// Symmetric (Newton's third law) fp32 variants, nbody_sym.cuh.  Selected with variant ids >= kSymBase.
+struct SymVariant {
+    const char* name;
+    int threads, r, tile, stages;
+    size_t smem;
+    const void* fn;
+};
+template <int THREADS, int R, int TILE, int STAGES, int UNROLL>
+SymVariant make_sym(const char* name) {
+    SymVariant v;
+    v.name = name;
+    v.threads = THREADS; v.r = R; v.tile = TILE; v.stages = STAGES;
+    v.smem = sym_smem_bytes<THREADS, R, TILE, STAGES>();
+    v.fn = (const void*)&sym_sweep_kernel<THREADS, R, TILE, STAGES, UNROLL>;
+    return v;
+}
+#define VSYM(T, R, TILE, ST, U) make_sym<T, R, TILE, ST, U>("f32sym_t" #T "_r" #R "_j" #TILE "_s" #ST "_u" #U)
+constexpr int kSymBase = 100;
+const std::vector<SymVariant>& variants_sym() {
+    static const std::vector<SymVariant> v = {
+        VSYM(256, 12, 512, 3, 2),   // 100 auto: large N on one GPU (IBLK 3072)
+        VSYM(256, 8, 512, 3, 4),    // 101 auto: power-of-two IBLK 2048 (shards of several GPUs)
+        VSYM(256, 8, 256, 3, 2),    // 102 auto: medium N
+        VSYM(256, 8, 512, 3, 2),    // 103
+        VSYM(256, 8, 512, 3, 1),    // 104
+        VSYM(256, 10, 512, 3, 2),   // 105
+        VSYM(128, 8, 256, 3, 2),    // 106
+        VSYM(256, 6, 512, 3, 2),    // 107
+        VSYM(256, 12, 512, 3, 1),   // 108
+        VSYM(256, 12, 512, 3, 4),   // 109
+        VSYM(256, 14, 512, 3, 2),   // 110
+        VSYM(256, 12, 256, 3, 2),   // 111
+        VSYM(256, 8, 256, 3, 4),    // 112
+        VSYM(256, 10, 256, 3, 2),   // 113
+        VSYM(256, 16, 512, 3, 1),   // 114
+    };
+    return v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // O(N) helper kernels: layout conversion between the reference's (N,3)+(N,) host arrays
 // (np2.py:63-66) and the device float4/double4 state.
@@ -225,8 +265,17 @@ struct gravb200_ctx {
     int* xerr = nullptr;                          // device flag: barrier timed out
     void* peer_pos[2][kMaxPeers + 1] = {};
     unsigned long long* peer_flags[kMaxPeers + 1] = {};
+    double* peer_acc[kMaxPeers + 1] = {};
     bool peer_is_ipc[kMaxPeers + 1] = {};
     unsigned long long epoch = 0;                 // barrier generation, advanced in lockstep on all ranks
+    // symmetric sweep (fp32): global fp64 accumulator and the flat-item offsets of the local block rows
+    double* acc64 = nullptr;
+    long long* row_start = nullptr;
+    size_t row_start_n = 0;
+    bool use_sym = false;
+    long long sym_min_n = 8192;    // automatic choice: symmetric sweep from this N on
+    int sym_variant = 0, sym_blocks = 0, sym_gblocks = 0;
+    long long sym_total = 0;
 };
 
 namespace {
@@ -261,7 +310,65 @@ long long grid_for(long long tiles, long long slots) {
 }
 
 // choose the variant and size its workspace
+// symmetric sweep set-up: block-row offsets, accumulator, grid
+int setup_sym(gravb200_ctx* c, int sv) {
+    const SymVariant& v = variants_sym()[sv];
+    const int iblk = v.threads * v.r;
+    const int Bt = (int)((c->n_total + iblk - 1) / iblk);
+    const int nib = (int)((c->n_local + iblk - 1) / iblk);
+    const int g0 = (int)(c->row0 / iblk);
+    std::vector<long long> rs((size_t)nib + 1, 0);
+    for (int i = 0; i < nib; ++i) rs[i + 1] = rs[i] + sym_row_tiles(c->n_total, iblk, v.tile, Bt, g0 + i);
+    if ((size_t)nib + 1 > c->row_start_n) {
+        if (c->row_start) CU(cudaFree(c->row_start));
+        c->row_start = nullptr;
+        CU(cudaMalloc(&c->row_start, ((size_t)nib + 1) * sizeof(long long)));
+        c->row_start_n = (size_t)nib + 1;
+    }
+    CU(cudaMemcpyAsync(c->row_start, rs.data(), ((size_t)nib + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));   // rs is a local
+    if (!c->acc64) {
+        CU(cudaMalloc(&c->acc64, (size_t)c->n_pad * 4 * sizeof(double)));
+        CU(cudaMemsetAsync(c->acc64, 0, (size_t)c->n_pad * 4 * sizeof(double), c->stream));
+    }
+    CU(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.fn, v.threads, v.smem));
+    if (occ < 1) return fail(GRAVB200_ECUDA, "symmetric variant %s does not fit on an SM", v.name);
+    c->sym_variant = sv;
+    c->sym_blocks = nib;
+    c->sym_gblocks = Bt;
+    c->sym_total = rs[nib];
+    c->occ = occ;
+    c->grid = (int)std::max<long long>(1, std::min<long long>((long long)occ * c->sm_count, rs[nib]));
+    c->use_sym = true;
+    return 0;
+}
+
 int pick_variant(gravb200_ctx* c) {
+    c->use_sym = false;
+    // symmetric sweep: forced (ids >= kSymBase) or automatic once there are enough body-blocks.  Several
+    // shards need the peer-store exchange (the owner of a row reads the other shards' partial sums over
+    // NVLink) and block-aligned shards.
+    if (c->dtype == GRAVB200_F32 && c->world == 1 && c->n_local > 0) {
+        int sv = -1;
+        if (c->forced_variant >= kSymBase) sv = c->forced_variant - kSymBase;
+        else if (c->forced_variant < 0 && c->n_total >= c->sym_min_n) sv = c->n_total >= 131072 ? 0 : 2;
+        if (sv >= 0) return setup_sym(c, sv);
+    } else if (c->dtype == GRAVB200_F32 && c->world > 1 && c->peer_mode && c->acc64) {
+        int sv = -1;
+        if (c->forced_variant >= kSymBase) sv = c->forced_variant - kSymBase;
+        else if (c->forced_variant < 0 && c->n_total >= 4 * c->sym_min_n) sv = 1;
+        if (sv >= 0) {
+            const SymVariant& v = variants_sym()[sv];
+            const long long iblk = (long long)v.threads * v.r;
+            if (c->chunk % iblk == 0 && c->n_local > 0) return setup_sym(c, sv);
+            if (c->forced_variant >= kSymBase)
+                return fail(GRAVB200_EINVAL, "symmetric variant %s needs shards that are multiples of %lld rows", v.name, iblk);
+        }
+    } else if (c->forced_variant >= kSymBase) {
+        return fail(GRAVB200_EINVAL, "symmetric variants need float32 and, on several shards, the peer-store exchange");
+    }
     const auto& vs = variants_of(c->dtype);
     const int n_auto = c->dtype == GRAVB200_F32 ? kAutoF32 : kAutoF64;
     int pick = n_auto - 1, occ = 0;
@@ -321,8 +428,57 @@ int pick_variant(gravb200_ctx* c) {
     return 0;
 }
 
+int peer_barrier(gravb200_ctx* c);
+
 int launch_sweep(gravb200_ctx* c, int integrate) {
     if (c->n_local <= 0 || c->grid <= 0) return 0;
+    if (c->use_sym) {
+        const SymVariant& sv = variants_sym()[c->sym_variant];
+        SymParams sp;
+        sp.pos_front = (const float4*)c->pos[c->front];
+        sp.acc64 = c->acc64;
+        sp.row_start = c->row_start;
+        sp.n_total = c->n_total;
+        sp.row0 = c->row0;
+        sp.n_local = c->n_local;
+        sp.n_iblocks = c->sym_blocks;
+        sp.n_gblocks = c->sym_gblocks;
+        sp.gblock0 = (int)(c->row0 / ((long long)sv.threads * sv.r));
+        sp.eps2_f = (float)(c->eps * c->eps);
+        sp.clk = c->clk;
+        void* sargs[] = {&sp};
+        CU(cudaLaunchKernel(sv.fn, dim3(c->grid), dim3(sv.threads), sargs, sv.smem, c->stream));
+        IntegrateParams ip;
+        memset(&ip, 0, sizeof(ip));
+        ip.sp.pos_front = c->pos[c->front];
+        ip.sp.pos_back = c->pos[c->front ^ 1];
+        ip.sp.vel_front = c->vel[c->front];
+        ip.sp.vel_back = c->vel[c->front ^ 1];
+        ip.sp.acc = c->acc;
+        ip.sp.n_total = c->n_total;
+        ip.sp.row0 = c->row0;
+        ip.sp.n_local = c->n_local;
+        ip.sp.G = c->G;
+        ip.sp.T = c->T;
+        ip.sp.integrate = integrate;
+        ip.sp.n_peers = 0;
+        ip.acc64 = c->acc64;
+        ip.n_src = 0;
+        if (c->world > 1) {
+            // every shard's sweep must be complete before the owners read the partial sums
+            int rc = peer_barrier(c);
+            if (rc) return rc;
+            for (int q = 0; q < c->world; ++q) {
+                ip.acc_src[ip.n_src++] = c->peer_acc[q];
+                if (q != c->rank) ip.sp.peer_back[ip.sp.n_peers++] = c->peer_pos[c->front ^ 1][q];
+            }
+        }
+        const unsigned gb = (unsigned)((c->n_local + 255) / 256);
+        sym_integrate_kernel<<<gb, 256, 0, c->stream>>>(ip);
+        CU(cudaGetLastError());
+        c->launches += 2;
+        return 0;
+    }
     const Variant& v = variants_of(c->dtype)[c->variant];
     SweepParams p;
     p.pos_front = c->pos[c->front];
@@ -380,7 +536,13 @@ int check_barrier_error(gravb200_ctx* c) {
 
 int exchange(gravb200_ctx* c) {
     if (c->world == 1) return 0;
-    if (c->peer_mode) return peer_barrier(c);   // the data already travelled in the sweep's epilogue
+    if (c->peer_mode) {   // the data already travelled in the sweep's epilogue
+        int rc = peer_barrier(c);
+        if (rc) return rc;
+        // symmetric sweep: all owners have read this shard's partial sums; clear them for the next step
+        if (c->use_sym) CU(cudaMemsetAsync(c->acc64, 0, (size_t)c->n_pad * 4 * sizeof(double), c->stream));
+        return 0;
+    }
     char* back = (char*)c->pos[c->front ^ 1];
     const size_t count = (size_t)c->chunk * 4;   // scalars per shard
     NC(g_nccl.AllGather(back + (size_t)c->rank * c->chunk * 4 * c->esz, back, count,
@@ -526,12 +688,16 @@ int gravb200_device_count(void) {
     return n;
 }
 
+int gravb200_sym_variant_count(void) { return (int)variants_sym().size(); }
+
 int gravb200_variant_count(int dtype) {
     if (dtype != GRAVB200_F32 && dtype != GRAVB200_F64) return 0;
     return (int)variants_of(dtype).size();
 }
 const char* gravb200_variant_name(int dtype, int variant) {
     if (dtype != GRAVB200_F32 && dtype != GRAVB200_F64) return "";
+    if (dtype == GRAVB200_F32 && variant >= kSymBase && variant - kSymBase < (int)variants_sym().size())
+        return variants_sym()[variant - kSymBase].name;
     const auto& vs = variants_of(dtype);
     if (variant < 0 || variant >= (int)vs.size()) return "";
     return vs[variant].name;
@@ -604,12 +770,16 @@ int gravb200_ctx_create(int64_t n_total, int dtype, int device, int rank, int wo
     CUX(cudaMemsetAsync(c->acc, 0, (size_t)c->chunk * v4, c->stream));
     CUX(cudaMalloc(&c->stage3, (size_t)n_total * 3 * c->esz));
     CUX(cudaMalloc(&c->stagem, (size_t)n_total * c->esz));
-    CUX(cudaMalloc(&c->clk, 2 * sizeof(unsigned long long)));
+    CUX(cudaMalloc(&c->clk, 2048 * sizeof(unsigned long long)));   // [0..1] CTA 0 cycles/ns, then per-CTA start/end stamps
     CUX(cudaMalloc(&c->flags, (kMaxPeers + 1) * sizeof(unsigned long long)));
     CUX(cudaMemsetAsync(c->flags, 0, (kMaxPeers + 1) * sizeof(unsigned long long), c->stream));
+    if (world > 1 && dtype == GRAVB200_F32) {   // symmetric sweep accumulator: must exist before peer_export
+        CUX(cudaMalloc(&c->acc64, (size_t)c->n_pad * 4 * sizeof(double)));
+        CUX(cudaMemsetAsync(c->acc64, 0, (size_t)c->n_pad * 4 * sizeof(double), c->stream));
+    }
     CUX(cudaMalloc(&c->xerr, sizeof(int)));
     CUX(cudaMemsetAsync(c->xerr, 0, sizeof(int), c->stream));
-    CUX(cudaMemsetAsync(c->clk, 0, 2 * sizeof(unsigned long long), c->stream));
+    CUX(cudaMemsetAsync(c->clk, 0, 2048 * sizeof(unsigned long long), c->stream));
 #undef CUX
     if (world > 1) {
         int rc = nccl_load();
@@ -648,8 +818,11 @@ int gravb200_ctx_destroy(gravb200_ctx* c) {
         for (int b = 0; b < 2; ++b)
             if (c->peer_pos[b][q]) cudaIpcCloseMemHandle(c->peer_pos[b][q]);
         if (c->peer_flags[q]) cudaIpcCloseMemHandle(c->peer_flags[q]);
+        if (c->peer_acc[q]) cudaIpcCloseMemHandle(c->peer_acc[q]);
     }
     if (c->flags) cudaFree(c->flags);
+    if (c->acc64) cudaFree(c->acc64);
+    if (c->row_start) cudaFree(c->row_start);
     if (c->xerr) cudaFree(c->xerr);
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
@@ -798,22 +971,34 @@ int gravb200_timings(gravb200_ctx* c, float* ms, int n) {
         unsigned long long h[2] = {0, 0};
         CU(cudaMemcpy(h, c->clk, sizeof(h), cudaMemcpyDeviceToHost));
         ms[3] = h[1] ? (float)((double)h[0] / (double)h[1] * 1e3) : -1.f;   // cycles/ns -> MHz
+        if (n > 4) ms[4] = (float)((double)h[1] * 1e-6);   // lifetime of CTA 0 of the last sweep, ms
     }
     return 0;
 }
 
 int gravb200_info(const gravb200_ctx* c, int64_t* info, int n) {
     if (!c || !info) return fail(GRAVB200_EINVAL, "ctx / info is NULL");
-    const Variant& v = variants_of(c->dtype)[c->variant];
-    const int64_t vals[11] = {c->grid, v.threads, v.r, v.tile, v.stages, (int64_t)v.smem,
-                              c->launches, c->sm_count, v.pack, c->occ, c->peer_mode ? 1 : 0};
-    for (int i = 0; i < n && i < 11; ++i) info[i] = vals[i];
+    int64_t vals[12];
+    if (c->use_sym) {
+        const SymVariant& v = variants_sym()[c->sym_variant];
+        const int64_t t[12] = {c->grid, v.threads, v.r, v.tile, v.stages, (int64_t)v.smem,
+                               c->launches, c->sm_count, 1, c->occ, c->peer_mode ? 1 : 0, kSymBase + c->sym_variant};
+        memcpy(vals, t, sizeof(t));
+    } else {
+        const Variant& v = variants_of(c->dtype)[c->variant];
+        const int64_t t[12] = {c->grid, v.threads, v.r, v.tile, v.stages, (int64_t)v.smem,
+                               c->launches, c->sm_count, v.pack, c->occ, c->peer_mode ? 1 : 0, c->variant};
+        memcpy(vals, t, sizeof(t));
+    }
+    for (int i = 0; i < n && i < 12; ++i) info[i] = vals[i];
     return 0;
 }
 
 int gravb200_set_variant(gravb200_ctx* c, int variant) {
     if (!c) return fail(GRAVB200_EINVAL, "ctx is NULL");
-    if (variant >= (int)variants_of(c->dtype).size()) return fail(GRAVB200_EINVAL, "variant %d out of range", variant);
+    if (variant >= kSymBase) {
+        if (variant - kSymBase >= (int)variants_sym().size()) return fail(GRAVB200_EINVAL, "variant %d out of range", variant);
+    } else if (variant >= (int)variants_of(c->dtype).size()) return fail(GRAVB200_EINVAL, "variant %d out of range", variant);
     if (c->pending) return fail(GRAVB200_EINVAL, "cannot switch variant between stage1 and stage2");
     CU(cudaSetDevice(c->device));
     c->forced_variant = variant < 0 ? -1 : variant;
@@ -830,6 +1015,7 @@ void* gravb200_device_ptr(gravb200_ctx* c, int which) {
         case 1: return c->pos[c->front ^ 1];
         case 2: return c->vel[c->front];
         case 3: return c->acc;
+        case 4: return c->clk;
         default: return nullptr;
     }
 }
@@ -837,8 +1023,8 @@ void* gravb200_device_ptr(gravb200_ctx* c, int which) {
 namespace {
 struct PeerBlob {   // what one shard publishes to the others (GRAVB200_PEER_BLOB_BYTES)
     int32_t pid, device, rank, world;
-    uint64_t pos[2], flags;   // raw device pointers, meaningful inside the owner's process
-    cudaIpcMemHandle_t h_pos[2], h_flags;
+    uint64_t pos[2], flags, acc64;   // raw device pointers, meaningful inside the owner's process
+    cudaIpcMemHandle_t h_pos[2], h_flags, h_acc64;
 };
 static_assert(sizeof(PeerBlob) <= GRAVB200_PEER_BLOB_BYTES, "peer blob size");
 }  // namespace
@@ -855,6 +1041,8 @@ int gravb200_peer_export(gravb200_ctx* c, void* blob) {
     b.pos[0] = (uint64_t)c->pos[0];
     b.pos[1] = (uint64_t)c->pos[1];
     b.flags = (uint64_t)c->flags;
+    b.acc64 = (uint64_t)c->acc64;
+    if (c->acc64) CU(cudaIpcGetMemHandle(&b.h_acc64, c->acc64));
     CU(cudaIpcGetMemHandle(&b.h_pos[0], c->pos[0]));
     CU(cudaIpcGetMemHandle(&b.h_pos[1], c->pos[1]));
     CU(cudaIpcGetMemHandle(&b.h_flags, c->flags));
@@ -875,6 +1063,7 @@ int gravb200_peer_connect(gravb200_ctx* c, const void* blobs) {
         if (b.rank != q || b.world != c->world) return fail(GRAVB200_EINVAL, "peer blob %d is from rank %d of %d", q, b.rank, b.world);
         if (q == c->rank) {
             c->peer_pos[0][q] = c->pos[0]; c->peer_pos[1][q] = c->pos[1]; c->peer_flags[q] = c->flags;
+            c->peer_acc[q] = c->acc64;
             continue;
         }
         if (b.pid == mypid) {
@@ -890,6 +1079,7 @@ int gravb200_peer_connect(gravb200_ctx* c, const void* blobs) {
             }
             c->peer_pos[0][q] = (void*)b.pos[0]; c->peer_pos[1][q] = (void*)b.pos[1];
             c->peer_flags[q] = (unsigned long long*)b.flags;
+            c->peer_acc[q] = (double*)b.acc64;
             c->peer_is_ipc[q] = false;
         } else {
             void* p0 = nullptr; void* p1 = nullptr; void* pf = nullptr;
@@ -897,6 +1087,11 @@ int gravb200_peer_connect(gravb200_ctx* c, const void* blobs) {
             CU(cudaIpcOpenMemHandle(&p1, b.h_pos[1], cudaIpcMemLazyEnablePeerAccess));
             CU(cudaIpcOpenMemHandle(&pf, b.h_flags, cudaIpcMemLazyEnablePeerAccess));
             c->peer_pos[0][q] = p0; c->peer_pos[1][q] = p1; c->peer_flags[q] = (unsigned long long*)pf;
+            if (b.acc64) {
+                void* pa = nullptr;
+                CU(cudaIpcOpenMemHandle(&pa, b.h_acc64, cudaIpcMemLazyEnablePeerAccess));
+                c->peer_acc[q] = (double*)pa;
+            }
             c->peer_is_ipc[q] = true;
         }
     }
@@ -911,6 +1106,10 @@ int gravb200_set_exchange_mode(gravb200_ctx* c, int mode) {
     if (mode == GRAVB200_XCHG_PEER && c->world > 1 && !c->peer_connected)
         return fail(GRAVB200_EINVAL, "peer-store exchange needs gravb200_peer_connect first");
     c->peer_mode = (mode == GRAVB200_XCHG_PEER) && c->world > 1;
+    CU(cudaSetDevice(c->device));
+    int rc = pick_variant(c);   // the symmetric sweep on several shards depends on the exchange mode
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

@@ -1,0 +1,394 @@
+// gravitation_b200 — symmetric (Newton's third law) fp32 sweep for sm_100a.
+//
+// The ordered sweep (nbody_kernels.cuh) evaluates every ordered pair: 12 packed FP32 operations + 2 MUFU
+// per pair of interactions, and it is bound by the operand fetch of the three accumulate FFMA2
+// (DESIGN.md section 3.1).  Here every UNORDERED pair {i, j} is evaluated once and applied to both bodies:
+//     d = r_j - r_i ;  w = |d|^-3 ;  a_i += m_j w d ;  a_j -= m_i w d
+// = 16 packed operations per pair of unordered pairs, i.e. 8 instead of 12 per ordered interaction — the
+// same trick the reference's CPU kernels use (py1.py:57-64, _lib1_/lib.c:75-124, _lib4_/lib.c:192-333).
+//
+// The j side needs a sum over the i-bodies of different lanes.  Instead of a shuffle-reduction per j-body,
+// the j-bodies travel: each lane holds ONE j-body of a 32-body chunk together with its packed partial
+// acceleration, interacts it with its R register-resident i-bodies, and passes both on to the next lane
+// (10 SHFL per step); after 32 steps every j-body is back home with its complete partial sum over the
+// warp's 32*R i-bodies (north_star (c): warp shuffles deliver the j-tile).  Per warp and step: 256
+// unordered pairs for 64 packed FP32 instructions + 8 MUFU + 10 SHFL (R = 8).
+//
+// Work decomposition: body-blocks of IBLK rows.  Block row I evaluates its own diagonal block ordered
+// (self pair masked by index, as in the ordered kernel) and, symmetrically, the column blocks I+1 .. I+H
+// (cyclically, H = half of the other blocks), so every block row carries the same amount of work whatever
+// rank owns it and every unordered pair of blocks is visited exactly once.  The flat list of (row, tile)
+// items is cut stream-K style into equal ranges, one per CTA.  Partial accelerations of both sides are
+// added into a global fp64 accumulator with RED.ADD.F64; `integrate_kernel` (O(N)) turns the accumulator
+// into a, v', r'.  The fp64 sums of fp32 tile partials are exact unless the partials of one body span
+// more than 2^29 in magnitude, so results are reproducible up to that rounding, not by construction.
+#pragma once
+
+#include "nbody_kernels.cuh"
+
+namespace gravb200 {
+
+struct SymParams {
+    const float4* pos_front;      // [n_pad] {x,y,z,m} of all bodies
+    double* acc64;                // [n_pad][4] fp64 accumulators, zero on entry
+    const long long* row_start;   // [n_iblocks + 1] flat tile offset of every local block row
+    long long n_total, row0, n_local;
+    int n_iblocks;                // local block rows
+    int n_gblocks;                // Bt: global body-blocks = ceil(n_total / IBLK)
+    int gblock0;                  // global index of local block row 0 (row0 / IBLK, row0 % IBLK == 0)
+    float eps2_f;
+    unsigned long long* clk;
+};
+
+// geometry helpers shared by host and device ---------------------------------------------------------
+__host__ __device__ inline int sym_tiles_in_block(long long n_total, int iblk, int tile, int K) {
+    long long cnt = n_total - (long long)K * iblk;
+    if (cnt > iblk) cnt = iblk;
+    return (int)((cnt + tile - 1) / tile);
+}
+// column blocks of block row Ig, the diagonal block included
+__host__ __device__ inline int sym_ncols(int Bt, int Ig) {
+    const int H = (Bt - 1) / 2;
+    const int extra = ((Bt & 1) == 0 && Ig < Bt / 2) ? 1 : 0;
+    return 1 + H + extra;
+}
+__host__ __device__ inline long long sym_row_tiles(long long n_total, int iblk, int tile, int Bt, int Ig) {
+    const int nc = sym_ncols(Bt, Ig);
+    const int D = iblk / tile;
+    long long t = (long long)nc * D;
+    const int dist_last = ((Bt - 1) - Ig + Bt) % Bt;   // where the (possibly short) last block sits in this row
+    if (dist_last < nc) t -= D - sym_tiles_in_block(n_total, iblk, tile, Bt - 1);
+    return t;
+}
+
+// position in the flat item list
+struct SymWalker {
+    int I;   // local block row
+    int c;   // column block within the row (0 = diagonal)
+    int t;   // tile within the column block
+};
+
+template <int IBLK, int TILE>
+__device__ __forceinline__ void sym_advance(SymWalker& w, const SymParams& p) {
+    const int Ig = p.gblock0 + w.I;
+    const int K = (Ig + w.c) % p.n_gblocks;
+    if (++w.t == sym_tiles_in_block(p.n_total, IBLK, TILE, K)) {
+        w.t = 0;
+        if (++w.c == sym_ncols(p.n_gblocks, Ig)) { w.c = 0; ++w.I; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// THREADS threads, R i-bodies per thread (even), TILE j-bodies per TMA stage (multiple of 32), STAGES.
+// Dynamic shared memory: tile ring | mbarriers | fp64 i-sums [3][R][THREADS] | j-partials [2][NWARPS][3][TILE].
+// ------------------------------------------------------------------------------------------------
+template <int THREADS, int R, int TILE, int STAGES, int UNROLL>
+__global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p) {
+    constexpr int IBLK = THREADS * R;
+    constexpr int NWARPS = THREADS / 32;
+    constexpr int P = R / 2;
+    constexpr int CHUNKS = TILE / 32;
+    static_assert(R % 2 == 0 && TILE % 32 == 0 && IBLK % TILE == 0, "geometry");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* tiles = reinterpret_cast<float4*>(smem_raw);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * TILE * sizeof(float4));
+    uint64_t* empty_bar = full_bar + STAGES;
+    double* ssum = reinterpret_cast<double*>(empty_bar + STAGES);                  // [3][R][THREADS]
+    float* jpart = reinterpret_cast<float*>(ssum + (size_t)3 * R * THREADS);       // [2][NWARPS][3][TILE]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long total = p.row_start[p.n_iblocks];
+    const long long S = gridDim.x;
+    const long long lo = sk_lo(total, blockIdx.x, S), hi = sk_lo(total, blockIdx.x + 1, S);
+    if (lo >= hi) return;
+    const int ntiles = (int)(hi - lo);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NWARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    unsigned long long clk0 = 0, ns0 = 0;
+    if (p.clk && tid == 0) {   // every CTA: start/end time stamps (debug: distribution of CTA lifetimes)
+        clk0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+    }
+
+    // locate flat item `lo`: block row by binary search over row_start, then walk the column blocks
+    SymWalker w0;
+    {
+        int a = 0, b = p.n_iblocks;   // row_start[a] <= lo < row_start[b]
+        while (b - a > 1) {
+            const int m = (a + b) >> 1;
+            if (p.row_start[m] <= lo) a = m; else b = m;
+        }
+        w0.I = a; w0.c = 0;
+        long long rem = lo - p.row_start[a];
+        const int Ig = p.gblock0 + a;
+        for (;;) {
+            const int tb = sym_tiles_in_block(p.n_total, IBLK, TILE, (Ig + w0.c) % p.n_gblocks);
+            if (rem < tb) break;
+            rem -= tb; ++w0.c;
+        }
+        w0.t = (int)rem;
+    }
+
+    // producer: flat order, its own walker
+    SymWalker pw = w0;
+    int p_slot = 0;
+    auto issue_next = [&]() {
+        const int K = (p.gblock0 + pw.I + pw.c) % p.n_gblocks;
+        const long long j0 = (long long)K * IBLK + (long long)pw.t * TILE;
+        long long cnt = p.n_total - j0;
+        if (cnt > TILE) cnt = TILE;
+        const uint32_t bytes = (uint32_t)(cnt * sizeof(float4));
+        mbar_expect_tx(&full_bar[p_slot], bytes);
+        tma_bulk_g2s(tiles + (size_t)p_slot * TILE, p.pos_front + j0, bytes, &full_bar[p_slot]);
+        sym_advance<IBLK, TILE>(pw, p);
+        if (++p_slot == STAGES) p_slot = 0;
+    };
+    if (tid == 0) {
+        const int pre = ntiles < (STAGES - 1) ? ntiles : (STAGES - 1);
+        for (int k = 0; k < pre; ++k) issue_next();
+    }
+
+    float xi[R], yi[R], zi[R];   // NEGATED positions of this thread's i-bodies (dx = xj + (-xi))
+    float2 mi[P];
+    SymWalker w = w0;
+    bool new_row = true;
+    int c_slot = 0, e_slot = 0;
+    uint32_t c_parity = 0, e_parity = 0;
+    int jbuf = 0;
+    const int src_lane = (lane + 1) & 31;
+
+    // flush this thread's i-side sums of the finished row segment into the global accumulator
+    auto flush_row = [&]() {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const long long il = (long long)w.I * IBLK + r * THREADS + tid;
+            if (il < p.n_local) {
+                double* dst = p.acc64 + (p.row0 + il) * 4;
+                atomicAdd(dst + 0, ssum[(0 * R + r) * THREADS + tid]);
+                atomicAdd(dst + 1, ssum[(1 * R + r) * THREADS + tid]);
+                atomicAdd(dst + 2, ssum[(2 * R + r) * THREADS + tid]);
+            }
+        }
+    };
+
+    for (int k = 0; k < ntiles; ++k) {
+        if (new_row) {
+            new_row = false;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const long long il = (long long)w.I * IBLK + r * THREADS + tid;
+                // padding rows sit far away with zero mass: d2 overflows to inf, rsqrt gives 0, nothing is added
+                float4 b = make_float4(1.0e30f, 1.0e30f, 1.0e30f, 0.f);
+                if (il < p.n_local) b = p.pos_front[p.row0 + il];
+                xi[r] = -b.x; yi[r] = -b.y; zi[r] = -b.z;
+                if (r & 1) mi[r >> 1].y = b.w; else mi[r >> 1].x = b.w;
+                ssum[(0 * R + r) * THREADS + tid] = 0.0;
+                ssum[(1 * R + r) * THREADS + tid] = 0.0;
+                ssum[(2 * R + r) * THREADS + tid] = 0.0;
+            }
+        }
+        if (tid == 0) {
+            const int kk = k + STAGES - 1;
+            if (kk < ntiles) {
+                if (kk >= STAGES) {
+                    mbar_wait(&empty_bar[e_slot], e_parity);
+                    if (++e_slot == STAGES) { e_slot = 0; e_parity ^= 1; }
+                }
+                issue_next();
+            }
+        }
+        const int s = c_slot;
+        mbar_wait(&full_bar[s], c_parity);
+        if (++c_slot == STAGES) { c_slot = 0; c_parity ^= 1; }
+        const float4* __restrict__ tile = tiles + (size_t)s * TILE;
+
+        const int Ig = p.gblock0 + w.I;
+        const int K = (Ig + w.c) % p.n_gblocks;
+        const long long j0 = (long long)K * IBLK + (long long)w.t * TILE;
+        long long cntl = p.n_total - j0;
+        const int jn = cntl > TILE ? TILE : (int)cntl;
+        const float e2 = p.eps2_f;
+
+        float2 ax[P], ay[P], az[P];
+#pragma unroll
+        for (int q = 0; q < P; ++q) ax[q] = ay[q] = az[q] = make_float2(0.f, 0.f);
+
+        if (w.c == 0) {
+            // diagonal block: ordered evaluation, j broadcast from shared memory, self pair masked by index
+            const int dj0 = (int)(j0 - ((long long)Ig * IBLK + tid));
+            auto ordered = [&](const float4 b, const int dj) {
+#pragma unroll
+                for (int q = 0; q < P; ++q) {
+                    const float2 dx = __fadd2_rn(make_float2(b.x, b.x), make_float2(xi[2 * q], xi[2 * q + 1]));
+                    const float2 dy = __fadd2_rn(make_float2(b.y, b.y), make_float2(yi[2 * q], yi[2 * q + 1]));
+                    const float2 dz = __fadd2_rn(make_float2(b.z, b.z), make_float2(zi[2 * q], zi[2 * q + 1]));
+                    float2 d2 = __ffma2_rn(dx, dx, make_float2(e2, e2));
+                    d2 = __ffma2_rn(dy, dy, d2);
+                    d2 = __ffma2_rn(dz, dz, d2);
+                    const float2 ri = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
+                    const float2 ri2 = __fmul2_rn(ri, ri);
+                    const float2 mr = __fmul2_rn(make_float2(b.w, b.w), ri);
+                    float2 sc = __fmul2_rn(mr, ri2);
+                    if (dj == (2 * q) * THREADS) sc.x = 0.f;
+                    if (dj == (2 * q + 1) * THREADS) sc.y = 0.f;
+                    ax[q] = __ffma2_rn(dx, sc, ax[q]);
+                    ay[q] = __ffma2_rn(dy, sc, ay[q]);
+                    az[q] = __ffma2_rn(dz, sc, az[q]);
+                }
+            };
+            if (jn == TILE) {
+#pragma unroll 2
+                for (int j = 0; j < TILE; ++j) ordered(tile[j], dj0 + j);
+            } else {
+#pragma unroll 1
+                for (int j = 0; j < jn; ++j) ordered(tile[j], dj0 + j);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+        } else {
+            // symmetric tile: ring over 32-body chunks
+            float* jp = jpart + ((size_t)jbuf * NWARPS + warp) * 3 * TILE;
+#pragma unroll 1
+            for (int c = 0; c < CHUNKS; ++c) {
+                const int jl = c * 32 + lane;
+                // padding j-bodies sit at the opposite far corner from padding i-bodies, so d2 is never 0
+                float4 bj = make_float4(-1.0e30f, -1.0e30f, -1.0e30f, 0.f);
+                if (jl < jn) bj = tile[jl];
+                if (c == CHUNKS - 1) {   // last read of this ring slot
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_bar[s]);
+                }
+                float2 jx = make_float2(0.f, 0.f), jy = jx, jz = jx;
+#pragma unroll UNROLL
+                for (int st = 0; st < 32; ++st) {
+#pragma unroll
+                    for (int q = 0; q < P; ++q) {
+                        const float2 dx = __fadd2_rn(make_float2(bj.x, bj.x), make_float2(xi[2 * q], xi[2 * q + 1]));
+                        const float2 dy = __fadd2_rn(make_float2(bj.y, bj.y), make_float2(yi[2 * q], yi[2 * q + 1]));
+                        const float2 dz = __fadd2_rn(make_float2(bj.z, bj.z), make_float2(zi[2 * q], zi[2 * q + 1]));
+                        float2 d2 = __ffma2_rn(dx, dx, make_float2(e2, e2));
+                        d2 = __ffma2_rn(dy, dy, d2);
+                        d2 = __ffma2_rn(dz, dz, d2);
+                        const float2 ri = make_float2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
+                        const float2 ri2 = __fmul2_rn(ri, ri);
+                        const float2 ri3 = __fmul2_rn(ri2, ri);
+                        const float2 si = __fmul2_rn(make_float2(bj.w, bj.w), ri3);
+                        const float2 sj = __fmul2_rn(mi[q], ri3);
+                        ax[q] = __ffma2_rn(dx, si, ax[q]);
+                        ay[q] = __ffma2_rn(dy, si, ay[q]);
+                        az[q] = __ffma2_rn(dz, si, az[q]);
+                        jx = __ffma2_rn(dx, sj, jx);
+                        jy = __ffma2_rn(dy, sj, jy);
+                        jz = __ffma2_rn(dz, sj, jz);
+                    }
+                    bj.x = __shfl_sync(0xffffffffu, bj.x, src_lane);
+                    bj.y = __shfl_sync(0xffffffffu, bj.y, src_lane);
+                    bj.z = __shfl_sync(0xffffffffu, bj.z, src_lane);
+                    bj.w = __shfl_sync(0xffffffffu, bj.w, src_lane);
+                    jx.x = __shfl_sync(0xffffffffu, jx.x, src_lane); jx.y = __shfl_sync(0xffffffffu, jx.y, src_lane);
+                    jy.x = __shfl_sync(0xffffffffu, jy.x, src_lane); jy.y = __shfl_sync(0xffffffffu, jy.y, src_lane);
+                    jz.x = __shfl_sync(0xffffffffu, jz.x, src_lane); jz.y = __shfl_sync(0xffffffffu, jz.y, src_lane);
+                }
+                // after 32 rotations every lane holds its own j-body again, with the sum over this warp's i-bodies
+                jp[0 * TILE + jl] = -(jx.x + jx.y);
+                jp[1 * TILE + jl] = -(jy.x + jy.y);
+                jp[2 * TILE + jl] = -(jz.x + jz.y);
+            }
+        }
+        // i side: fp32 tile sums into this thread's fp64 sums
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            ssum[(0 * R + 2 * q) * THREADS + tid] += (double)ax[q].x;
+            ssum[(0 * R + 2 * q + 1) * THREADS + tid] += (double)ax[q].y;
+            ssum[(1 * R + 2 * q) * THREADS + tid] += (double)ay[q].x;
+            ssum[(1 * R + 2 * q + 1) * THREADS + tid] += (double)ay[q].y;
+            ssum[(2 * R + 2 * q) * THREADS + tid] += (double)az[q].x;
+            ssum[(2 * R + 2 * q + 1) * THREADS + tid] += (double)az[q].y;
+        }
+        if (w.c != 0) {
+            // j side: combine the warps in a fixed order, then one RED.ADD.F64 per body and component.
+            // jpart is double buffered, so one CTA barrier per symmetric tile is enough.
+            __syncthreads();
+            const float* jb = jpart + (size_t)jbuf * NWARPS * 3 * TILE;
+            for (int j = tid; j < jn; j += THREADS) {
+                double sx = 0.0, sy = 0.0, sz = 0.0;
+#pragma unroll
+                for (int wv = 0; wv < NWARPS; ++wv) {
+                    sx += (double)jb[(wv * 3 + 0) * TILE + j];
+                    sy += (double)jb[(wv * 3 + 1) * TILE + j];
+                    sz += (double)jb[(wv * 3 + 2) * TILE + j];
+                }
+                double* dst = p.acc64 + (j0 + j) * 4;
+                atomicAdd(dst + 0, sx);
+                atomicAdd(dst + 1, sy);
+                atomicAdd(dst + 2, sz);
+            }
+            jbuf ^= 1;
+        }
+
+        const int rowI = w.I;
+        sym_advance<IBLK, TILE>(w, p);
+        if (w.I != rowI || k == ntiles - 1) {
+            const SymWalker keep = w;
+            w.I = rowI;
+            flush_row();
+            w = keep;
+            new_row = true;
+        }
+    }
+    if (p.clk && tid == 0) {
+        unsigned long long ns1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+        if (blockIdx.x == 0) { p.clk[0] = clock64() - clk0; p.clk[1] = ns1 - ns0; }
+        if (blockIdx.x < 1022) { p.clk[2 + 2 * blockIdx.x] = ns0; p.clk[3 + 2 * blockIdx.x] = ns1; }
+    }
+}
+
+template <int THREADS, int R, int TILE, int STAGES>
+constexpr size_t sym_smem_bytes() {
+    return (size_t)STAGES * TILE * sizeof(float4) + 2 * STAGES * sizeof(uint64_t) + (size_t)3 * R * THREADS * sizeof(double) +
+           (size_t)2 * (THREADS / 32) * 3 * TILE * sizeof(float);
+}
+
+// ------------------------------------------------------------------------------------------------
+// O(N) second half of a symmetric step: accumulator -> a, v', r' for this shard's rows, accumulator
+// cleared for the next step.  Same separately rounded stage-2 arithmetic as the fused epilogue
+// (finalize_body, np2.py:110-115), including the peer stores of the fused position exchange.
+// ------------------------------------------------------------------------------------------------
+struct IntegrateParams {
+    SweepParams sp;      // pos/vel/acc buffers, G, T, row0, n_local, peers
+    double* acc64;       // [n_pad][4] this shard's accumulator
+    // several shards: every shard accumulated partial sums for ALL bodies; the owner of a row adds the
+    // partials of all shards in rank order (own memory + NVLink peer loads) — a reduce-scatter fused into
+    // the integrate kernel.  n_src == 0: single shard, read and clear acc64.
+    int n_src;
+    const double* acc_src[kMaxPeers + 1];
+};
+
+__global__ void sym_integrate_kernel(const IntegrateParams q) {
+    const long long il = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (il >= q.sp.n_local) return;
+    double sx, sy, sz;
+    if (q.n_src == 0) {
+        double4* src = reinterpret_cast<double4*>(q.acc64) + (q.sp.row0 + il);
+        const double4 s = *src;
+        *src = make_double4(0.0, 0.0, 0.0, 0.0);
+        sx = s.x; sy = s.y; sz = s.z;
+    } else {
+        sx = sy = sz = 0.0;
+        for (int r = 0; r < q.n_src; ++r) {   // the accumulators are cleared after the step barrier (host side)
+            const double4 s = ld_cg_d4(reinterpret_cast<const double4*>(q.acc_src[r]) + (q.sp.row0 + il));
+            sx += s.x; sy += s.y; sz += s.z;
+        }
+    }
+    const float4 ri = reinterpret_cast<const float4*>(q.sp.pos_front)[q.sp.row0 + il];
+    finalize_body(q.sp, il, sx, sy, sz, ri, 0.f);
+}
+
+}  // namespace gravb200

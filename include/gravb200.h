@@ -34,7 +34,7 @@ extern "C" {
 #define GRAVB200_ENODEV (-4)  /* no CUDA device */
 
 #define GRAVB200_NCCL_ID_BYTES 128
-#define GRAVB200_PEER_BLOB_BYTES 256
+#define GRAVB200_PEER_BLOB_BYTES 512
 #define GRAVB200_XCHG_NCCL 0 /* per-step in-place ncclAllGather of the new positions */
 #define GRAVB200_XCHG_PEER 1 /* fused: the sweep's epilogue stores r' into every peer over NVLink + flag barrier */
 
@@ -99,17 +99,20 @@ int gravb200_shard(const gravb200_ctx* ctx, int64_t* row0, int64_t* n_local);
 
 /* Device-side timings (cudaEvent): ms[0] = last stage1 sweep kernel, ms[1] = last exchange,
  * ms[2] = total of the last gravb200_steps() call, ms[3] = SM clock (MHz) that CTA 0 of the last sweep
- * observed over its lifetime (clock64 / globaltimer); n = capacity of ms. */
+ * observed over its lifetime (clock64 / globaltimer), ms[4] = that lifetime in ms; n = capacity of ms. */
 int gravb200_timings(gravb200_ctx* ctx, float* ms, int n);
 
 /* Introspection used by bench.py / tests: launch geometry and counters.
  * info[0]=grid, [1]=threads, [2]=i-bodies per thread, [3]=j tile, [4]=stages, [5]=dynamic smem bytes,
  * [6]=kernel launches so far, [7]=SM count, [8]=packed f32x2 (1/0), [9]=resident CTAs per SM,
- * [10]=exchange mode (GRAVB200_XCHG_*). */
+ * [10]=exchange mode (GRAVB200_XCHG_*), [11]=variant id in use. */
 int gravb200_info(const gravb200_ctx* ctx, int64_t* info, int n);
-/* Force a kernel variant (tests / ncu A-B): variant < 0 restores the automatic choice. */
+/* Force a kernel variant (tests / ncu A-B): variant < 0 restores the automatic choice.  Ids 0 .. count-1 are
+ * the ordered sweeps (bit-reproducible), ids 100 + k, k < gravb200_sym_variant_count(), the symmetric fp32 sweeps
+ * (every unordered pair once, fp64 atomics: reproducible up to fp64 rounding of the cross-tile sum). */
 int gravb200_set_variant(gravb200_ctx* ctx, int variant);
 int gravb200_variant_count(int dtype);
+int gravb200_sym_variant_count(void);
 const char* gravb200_variant_name(int dtype, int variant);
 
 /* Raw device pointers of the shard state (for peer access / torch interop in tests).

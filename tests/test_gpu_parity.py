@@ -108,11 +108,13 @@ def test_every_kernel_variant_agrees_with_the_oracle(dtype, oracle, gpu):
 	n = 3001
 	r, v, m, G, T = oracle.uniform_universe(n, 7, dtype)
 	ref = oracle.stage1_f64(r, m, G)
-	names = gpu.variant_names(dtype)
-	for vi, name in enumerate(names):
+	ids = [(vi, name) for vi, name in enumerate(gpu.variant_names(dtype))]
+	if dtype == 'float32': # the symmetric sweeps (every unordered pair once) have ids SYM_BASE + k
+		ids += [(gpu.SYM_BASE + k, name) for k, name in enumerate(gpu.sym_variant_names())]
+	for vi, name in ids:
 		a, info = run_stage1(gpu, r, v, m, G, T, dtype, variant = vi)
 		assert oracle.max_rel_err(a, ref) <= TOL_ACC[dtype], name
-		assert info['grid'] >= 1
+		assert info['grid'] >= 1 and info['variant'] == vi
 
 
 @pytest.mark.parametrize('dtype', DTYPES)
@@ -168,6 +170,7 @@ def test_steps_equals_repeated_stage_calls_and_is_deterministic(dtype, oracle, g
 	for mode in ('stages', 'steps', 'steps'):
 		sh = gpu.Shard(n, dtype)
 		sh.upload(r, v, m, G, T)
+		sh.set_variant(1) # an ordered sweep: fixed-order combination, bit-reproducible by construction
 		if mode == 'stages':
 			for _ in range(5):
 				sh.stage1(); sh.stage2()
@@ -230,11 +233,15 @@ def test_full_size_properties(dtype, n, oracle, gpu):
 	a64, m64 = a.astype(np.float64), m.astype(np.float64)
 	net = np.linalg.norm((a64 * m64[:, None]).sum(0)) / (np.linalg.norm(a64, axis = 1) * m64).sum()
 	assert net <= (1e-6 if dtype == 'float32' else 1e-13)
-	# doubling every mass (a power of two) must double every acceleration bit for bit; same for G
+	# doubling every mass (a power of two) doubles every partial sum exactly; the symmetric fp32 sweep adds
+	# its fp64 partials with atomics (order not fixed), so allow the last fp64 rounding to differ
 	sh.upload(r, v, (m * 2).astype(dtype), G, T)
 	sh.stage1(); sh.sync()
 	_, _, a_m2 = sh.download(r = False, v = False, a = True)
-	assert np.array_equal(a_m2, a * np.array(2, dtype))
+	if sh.info()['variant'] >= gpu.SYM_BASE:
+		assert np.allclose(a_m2, a * np.array(2, dtype), rtol = 3e-7, atol = 0.0)
+	else:
+		assert np.array_equal(a_m2, a * np.array(2, dtype))
 	sh.close()
 
 
@@ -399,3 +406,50 @@ def test_accuracy_command_float32_against_float64(gpu):
 	out = accuracy.main(['-k', 'b200', '--dtype', 'float32', '--ref_dtype', 'float64', '-n', '1024', '-s', '5'])
 	assert out['bodies'] == 1024
 	assert out['acceleration_max_rel'] <= 1e-4 and out['position_max_rel'] <= 5e-6 and out['velocity_max_rel'] <= 5e-6
+
+
+@pytest.mark.parametrize('n', (8192, 10007, 40000))
+def test_symmetric_sweep_parity_and_reproducibility(n, oracle, gpu):
+	"""the default fp32 path from N = 8192 on: every unordered pair once (nbody_sym.cuh).  Parity against
+	the float64 oracle, bit-exact stage 2, and run-to-run agreement (fp64 atomics: reproducible up to the
+	rounding of the cross-tile fp64 sum, far below float32 resolution)"""
+	r, v, m, G, T = oracle.uniform_universe(n, 77, 'float32')
+	v = (np.random.default_rng(2).standard_normal((n, 3)) * 1e-5).astype(np.float32)
+	ref = oracle.stage1_f64(r, m, G)
+	outs = []
+	for _ in range(2):
+		sh = gpu.Shard(n, 'float32')
+		sh.upload(r, v, m, G, T)
+		assert sh.info()['variant'] >= gpu.SYM_BASE
+		sh.stage1(); sh.stage2()
+		outs.append(sh.download(a = True))
+		sh.close()
+	rr, vv, aa = outs[0]
+	assert oracle.max_rel_err(aa, ref) <= 1e-4
+	r_ref, v_ref = r.copy(), v.copy()
+	oracle.stage2(r_ref, v_ref, aa, T)
+	assert np.array_equal(rr, r_ref) and np.array_equal(vv, v_ref)
+	assert np.allclose(outs[1][2], aa, rtol = 3e-7, atol = 0.0)
+
+
+def test_symmetric_sweep_on_two_gpus(oracle, gpu):
+	"""several shards: every shard sweeps its block rows symmetrically into a full-size accumulator, the
+	owner of a row adds all shards' partial sums over NVLink inside the integrate kernel"""
+	if gpu.device_count() < 2:
+		pytest.skip('needs 2 GPUs')
+	from gravitation_b200.kernel import b200
+	n = 32768
+	r, v, m, G, T = oracle.uniform_universe(n, 12, 'float64')
+	u = b200.universe(T = T, G = G, scale_off = True, dtype = 'float32', threads = 2)
+	u.add_objects(r, v, m, scale_off = True)
+	u.start()
+	assert all(sh.info()['variant'] >= gpu.SYM_BASE and sh.info()['exchange_mode'] == gpu.XCHG_PEER for sh in u._shards)
+	u.step_stage1()
+	a = np.array(u.accelerations())
+	assert oracle.max_rel_err(a, oracle.stage1_f64(r.astype(np.float32), m.astype(np.float32), G)) <= 1e-4
+	u.step_stage2(); u.step_stage3()
+	u.steps(2)
+	r3 = np.array([pm._r for pm in u])
+	u.stop()
+	r_ref, _ = oracle.steps(r, v, m, G, T, 3)
+	assert traj_err(r3, r_ref) <= 5e-6
