@@ -256,9 +256,9 @@ def own_arm(args):
 			traffic = None
 	symmetric = info.get('variant', 0) >= _shim.SYM_BASE
 	# executed work per ORDERED interaction (the metric's unit): ordered sweep 12 FP32-pipe lane-ops = 19 FLOP,
-	# symmetric sweep (every unordered pair once, both bodies updated) 8 lane-ops = 13 FLOP; fp64 sweep 16 ops
-	lane_ops = (8.0 if symmetric else 12.0) if dtype == 'float32' else 16.0
-	flop_exec = (13.0 if symmetric else 19.0) if dtype == 'float32' else 29.0
+	# symmetric sweep (every unordered pair once, both bodies updated) 8 lane-ops = 13 FLOP; fp64: 16 / 10 ops
+	lane_ops = (8.0 if symmetric else 12.0) if dtype == 'float32' else (10.0 if symmetric else 16.0)
+	flop_exec = (13.0 if symmetric else 19.0) if dtype == 'float32' else (16.0 if symmetric else 25.0)
 	pipe_ceiling = sm_count * lanes * sm_max * 1e6 / lane_ops / 1e9   # G interactions/s if the FP pipe never idled
 	roofline = {
 		'bound': 'fp32_fma' if dtype == 'float32' else 'fp64_fma',

@@ -55,7 +55,7 @@ _SIGNATURES = [
 	('gravb200_info', ctypes.c_int, [_c_ctx, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
 	('gravb200_set_variant', ctypes.c_int, [_c_ctx, ctypes.c_int]),
 	('gravb200_variant_count', ctypes.c_int, [ctypes.c_int]),
-	('gravb200_sym_variant_count', ctypes.c_int, []),
+	('gravb200_sym_variant_count', ctypes.c_int, [ctypes.c_int]),
 	('gravb200_variant_name', ctypes.c_char_p, [ctypes.c_int, ctypes.c_int]),
 	('gravb200_device_ptr', ctypes.c_void_p, [_c_ctx, ctypes.c_int]),
 	('gravb200_host_alloc', ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
@@ -150,10 +150,11 @@ def variant_names(dtype = 'float32'):
 	return [lib.gravb200_variant_name(d, i).decode() for i in range(lib.gravb200_variant_count(d))]
 
 
-def sym_variant_names():
-	"""symmetric fp32 sweeps (ids SYM_BASE + k)"""
+def sym_variant_names(dtype = 'float32'):
+	"""symmetric sweeps of `dtype` (ids SYM_BASE + k)"""
 	lib = load()
-	return [lib.gravb200_variant_name(F32, SYM_BASE + k).decode() for k in range(lib.gravb200_sym_variant_count())]
+	d = _DTYPES[dtype]
+	return [lib.gravb200_variant_name(d, SYM_BASE + k).decode() for k in range(lib.gravb200_sym_variant_count(d))]
 
 
 class PinnedArray:

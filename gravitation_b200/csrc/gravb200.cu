@@ -202,6 +202,34 @@ const std::vector<SymVariant>& variants_sym() {
     return v;
 }
 
+template <int THREADS, int R, int TILE, int STAGES, int MINB, int UNROLL>
+SymVariant make_sym64(const char* name) {
+    SymVariant v;
+    v.name = name;
+    v.threads = THREADS; v.r = R; v.tile = TILE; v.stages = STAGES;
+    v.smem = sym64_smem_bytes<THREADS, TILE, STAGES>();
+    v.fn = (const void*)&sym_sweep_kernel_f64<THREADS, R, TILE, STAGES, MINB, UNROLL>;
+    return v;
+}
+#define VSYM64(T, R, TILE, ST, MB, U) make_sym64<T, R, TILE, ST, MB, U>("f64sym_t" #T "_r" #R "_j" #TILE "_s" #ST "_b" #MB "_u" #U)
+const std::vector<SymVariant>& variants_sym64() {
+    static const std::vector<SymVariant> v = {
+        VSYM64(256, 6, 256, 3, 1, 2),   // 100 auto: one GPU, N >= 2^15 (IBLK 1536)
+        VSYM64(256, 8, 256, 3, 1, 1),   // 101 auto: power-of-two IBLK 2048 (shards of several GPUs)
+        VSYM64(256, 4, 128, 3, 2, 2),   // 102 auto: medium N (IBLK 1024)
+        VSYM64(256, 4, 256, 3, 2, 2),   // 103
+        VSYM64(256, 4, 256, 3, 2, 1),   // 104
+        VSYM64(256, 2, 256, 3, 2, 2),   // 105
+        VSYM64(128, 4, 128, 3, 4, 2),   // 106
+        VSYM64(256, 6, 256, 3, 1, 1),   // 107
+        VSYM64(256, 6, 128, 3, 1, 2),   // 108
+        VSYM64(256, 8, 128, 3, 1, 1),   // 109
+        VSYM64(256, 8, 256, 3, 1, 2),   // 110
+    };
+    return v;
+}
+const std::vector<SymVariant>& variants_sym_of(int dtype) { return dtype == GRAVB200_F32 ? variants_sym() : variants_sym64(); }
+
 // ---------------------------------------------------------------------------------------------
 // O(N) helper kernels: layout conversion between the reference's (N,3)+(N,) host arrays
 // (np2.py:63-66) and the device float4/double4 state.
@@ -312,7 +340,7 @@ long long grid_for(long long tiles, long long slots) {
 // choose the variant and size its workspace
 // symmetric sweep set-up: block-row offsets, accumulator, grid
 int setup_sym(gravb200_ctx* c, int sv) {
-    const SymVariant& v = variants_sym()[sv];
+    const SymVariant& v = variants_sym_of(c->dtype)[sv];
     const int iblk = v.threads * v.r;
     const int Bt = (int)((c->n_total + iblk - 1) / iblk);
     const int nib = (int)((c->n_local + iblk - 1) / iblk);
@@ -350,24 +378,27 @@ int pick_variant(gravb200_ctx* c) {
     // symmetric sweep: forced (ids >= kSymBase) or automatic once there are enough body-blocks.  Several
     // shards need the peer-store exchange (the owner of a row reads the other shards' partial sums over
     // NVLink) and block-aligned shards.
-    if (c->dtype == GRAVB200_F32 && c->world == 1 && c->n_local > 0) {
+    const int n_sym = (int)variants_sym_of(c->dtype).size();
+    if (c->forced_variant >= kSymBase + n_sym) return fail(GRAVB200_EINVAL, "variant %d out of range", c->forced_variant);
+    if (c->world == 1 && c->n_local > 0) {
         int sv = -1;
         if (c->forced_variant >= kSymBase) sv = c->forced_variant - kSymBase;
-        else if (c->forced_variant < 0 && c->n_total >= c->sym_min_n) sv = c->n_total >= 131072 ? 0 : 2;
+        else if (c->forced_variant < 0 && c->n_total >= c->sym_min_n)
+            sv = c->dtype == GRAVB200_F32 ? (c->n_total >= 131072 ? 0 : 2) : (c->n_total >= 32768 ? 0 : 2);
         if (sv >= 0) return setup_sym(c, sv);
-    } else if (c->dtype == GRAVB200_F32 && c->world > 1 && c->peer_mode && c->acc64) {
+    } else if (c->world > 1 && c->peer_mode && c->acc64) {
         int sv = -1;
         if (c->forced_variant >= kSymBase) sv = c->forced_variant - kSymBase;
         else if (c->forced_variant < 0 && c->n_total >= 4 * c->sym_min_n) sv = 1;
         if (sv >= 0) {
-            const SymVariant& v = variants_sym()[sv];
+            const SymVariant& v = variants_sym_of(c->dtype)[sv];
             const long long iblk = (long long)v.threads * v.r;
             if (c->chunk % iblk == 0 && c->n_local > 0) return setup_sym(c, sv);
             if (c->forced_variant >= kSymBase)
                 return fail(GRAVB200_EINVAL, "symmetric variant %s needs shards that are multiples of %lld rows", v.name, iblk);
         }
     } else if (c->forced_variant >= kSymBase) {
-        return fail(GRAVB200_EINVAL, "symmetric variants need float32 and, on several shards, the peer-store exchange");
+        return fail(GRAVB200_EINVAL, "on several shards the symmetric variants need the peer-store exchange");
     }
     const auto& vs = variants_of(c->dtype);
     const int n_auto = c->dtype == GRAVB200_F32 ? kAutoF32 : kAutoF64;
@@ -433,9 +464,11 @@ int peer_barrier(gravb200_ctx* c);
 int launch_sweep(gravb200_ctx* c, int integrate) {
     if (c->n_local <= 0 || c->grid <= 0) return 0;
     if (c->use_sym) {
-        const SymVariant& sv = variants_sym()[c->sym_variant];
+        const SymVariant& sv = variants_sym_of(c->dtype)[c->sym_variant];
         SymParams sp;
         sp.pos_front = (const float4*)c->pos[c->front];
+        sp.pos_front_d = (const double4*)c->pos[c->front];
+        sp.eps2_d = c->eps * c->eps;
         sp.acc64 = c->acc64;
         sp.row_start = c->row_start;
         sp.n_total = c->n_total;
@@ -474,7 +507,8 @@ int launch_sweep(gravb200_ctx* c, int integrate) {
             }
         }
         const unsigned gb = (unsigned)((c->n_local + 255) / 256);
-        sym_integrate_kernel<<<gb, 256, 0, c->stream>>>(ip);
+        if (c->dtype == GRAVB200_F32) sym_integrate_kernel<float><<<gb, 256, 0, c->stream>>>(ip);
+        else sym_integrate_kernel<double><<<gb, 256, 0, c->stream>>>(ip);
         CU(cudaGetLastError());
         c->launches += 2;
         return 0;
@@ -688,7 +722,10 @@ int gravb200_device_count(void) {
     return n;
 }
 
-int gravb200_sym_variant_count(void) { return (int)variants_sym().size(); }
+int gravb200_sym_variant_count(int dtype) {
+    if (dtype != GRAVB200_F32 && dtype != GRAVB200_F64) return 0;
+    return (int)variants_sym_of(dtype).size();
+}
 
 int gravb200_variant_count(int dtype) {
     if (dtype != GRAVB200_F32 && dtype != GRAVB200_F64) return 0;
@@ -696,8 +733,8 @@ int gravb200_variant_count(int dtype) {
 }
 const char* gravb200_variant_name(int dtype, int variant) {
     if (dtype != GRAVB200_F32 && dtype != GRAVB200_F64) return "";
-    if (dtype == GRAVB200_F32 && variant >= kSymBase && variant - kSymBase < (int)variants_sym().size())
-        return variants_sym()[variant - kSymBase].name;
+    if (variant >= kSymBase && variant - kSymBase < (int)variants_sym_of(dtype).size())
+        return variants_sym_of(dtype)[variant - kSymBase].name;
     const auto& vs = variants_of(dtype);
     if (variant < 0 || variant >= (int)vs.size()) return "";
     return vs[variant].name;
@@ -773,7 +810,7 @@ int gravb200_ctx_create(int64_t n_total, int dtype, int device, int rank, int wo
     CUX(cudaMalloc(&c->clk, 2048 * sizeof(unsigned long long)));   // [0..1] CTA 0 cycles/ns, then per-CTA start/end stamps
     CUX(cudaMalloc(&c->flags, (kMaxPeers + 1) * sizeof(unsigned long long)));
     CUX(cudaMemsetAsync(c->flags, 0, (kMaxPeers + 1) * sizeof(unsigned long long), c->stream));
-    if (world > 1 && dtype == GRAVB200_F32) {   // symmetric sweep accumulator: must exist before peer_export
+    if (world > 1) {   // symmetric sweep accumulator: must exist before peer_export
         CUX(cudaMalloc(&c->acc64, (size_t)c->n_pad * 4 * sizeof(double)));
         CUX(cudaMemsetAsync(c->acc64, 0, (size_t)c->n_pad * 4 * sizeof(double), c->stream));
     }
@@ -980,7 +1017,7 @@ int gravb200_info(const gravb200_ctx* c, int64_t* info, int n) {
     if (!c || !info) return fail(GRAVB200_EINVAL, "ctx / info is NULL");
     int64_t vals[12];
     if (c->use_sym) {
-        const SymVariant& v = variants_sym()[c->sym_variant];
+        const SymVariant& v = variants_sym_of(c->dtype)[c->sym_variant];
         const int64_t t[12] = {c->grid, v.threads, v.r, v.tile, v.stages, (int64_t)v.smem,
                                c->launches, c->sm_count, 1, c->occ, c->peer_mode ? 1 : 0, kSymBase + c->sym_variant};
         memcpy(vals, t, sizeof(t));
@@ -997,7 +1034,7 @@ int gravb200_info(const gravb200_ctx* c, int64_t* info, int n) {
 int gravb200_set_variant(gravb200_ctx* c, int variant) {
     if (!c) return fail(GRAVB200_EINVAL, "ctx is NULL");
     if (variant >= kSymBase) {
-        if (variant - kSymBase >= (int)variants_sym().size()) return fail(GRAVB200_EINVAL, "variant %d out of range", variant);
+        if (variant - kSymBase >= (int)variants_sym_of(c->dtype).size()) return fail(GRAVB200_EINVAL, "variant %d out of range", variant);
     } else if (variant >= (int)variants_of(c->dtype).size()) return fail(GRAVB200_EINVAL, "variant %d out of range", variant);
     if (c->pending) return fail(GRAVB200_EINVAL, "cannot switch variant between stage1 and stage2");
     CU(cudaSetDevice(c->device));

@@ -29,7 +29,8 @@
 namespace gravb200 {
 
 struct SymParams {
-    const float4* pos_front;      // [n_pad] {x,y,z,m} of all bodies
+    const float4* pos_front;      // [n_pad] {x,y,z,m} of all bodies (fp32 kernel)
+    const double4* pos_front_d;   // same, fp64 kernel
     double* acc64;                // [n_pad][4] fp64 accumulators, zero on entry
     const long long* row_start;   // [n_iblocks + 1] flat tile offset of every local block row
     long long n_total, row0, n_local;
@@ -37,6 +38,7 @@ struct SymParams {
     int n_gblocks;                // Bt: global body-blocks = ceil(n_total / IBLK)
     int gblock0;                  // global index of local block row 0 (row0 / IBLK, row0 % IBLK == 0)
     float eps2_f;
+    double eps2_d;
     unsigned long long* clk;
 };
 
@@ -357,6 +359,231 @@ constexpr size_t sym_smem_bytes() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// fp64 twin.  No packing (there are no packed FP64 instructions); R i-bodies per thread, sums stay in fp64
+// registers for the whole block row.  Per unordered pair: 3 DADD + 3 DFMA + 6 (MUFU.RSQ64H seed refined to
+// |d|^-3, see mass_over_r3) + 2 (both masses) + 6 DFMA = 20 FP64-pipe operations, i.e. 10 per ordered
+// interaction instead of the ordered sweep's 16.  14 32-bit SHFL move the j-body and its partials.
+// Dynamic shared memory: tile ring | mbarriers | j-partials [NWARPS][3][TILE] doubles (single buffered, two
+// CTA barriers per tile: a tile takes ~50 us).
+// Padding bodies sit at +-1e150: d2 stays finite, the refined |d|^-3 underflows to 0 (inf would give
+// inf * 0 = NaN in the refinement).
+// ------------------------------------------------------------------------------------------------
+template <int THREADS, int R, int TILE, int STAGES, int MINB, int UNROLL>
+__global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymParams p) {
+    constexpr int IBLK = THREADS * R;
+    constexpr int NWARPS = THREADS / 32;
+    constexpr int CHUNKS = TILE / 32;
+    static_assert(TILE % 32 == 0 && IBLK % TILE == 0, "geometry");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double4* tiles = reinterpret_cast<double4*>(smem_raw);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * TILE * sizeof(double4));
+    uint64_t* empty_bar = full_bar + STAGES;
+    double* jpart = reinterpret_cast<double*>(empty_bar + STAGES);   // [NWARPS][3][TILE]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long total = p.row_start[p.n_iblocks];
+    const long long S = gridDim.x;
+    const long long lo = sk_lo(total, blockIdx.x, S), hi = sk_lo(total, blockIdx.x + 1, S);
+    if (lo >= hi) return;
+    const int ntiles = (int)(hi - lo);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NWARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    unsigned long long clk0 = 0, ns0 = 0;
+    if (p.clk && blockIdx.x == 0 && tid == 0) {
+        clk0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+    }
+
+    SymWalker w0;
+    {
+        int a = 0, b = p.n_iblocks;
+        while (b - a > 1) {
+            const int m = (a + b) >> 1;
+            if (p.row_start[m] <= lo) a = m; else b = m;
+        }
+        w0.I = a; w0.c = 0;
+        long long rem = lo - p.row_start[a];
+        const int Ig = p.gblock0 + a;
+        for (;;) {
+            const int tb = sym_tiles_in_block(p.n_total, IBLK, TILE, (Ig + w0.c) % p.n_gblocks);
+            if (rem < tb) break;
+            rem -= tb; ++w0.c;
+        }
+        w0.t = (int)rem;
+    }
+
+    SymWalker pw = w0;
+    int p_slot = 0;
+    auto issue_next = [&]() {
+        const int K = (p.gblock0 + pw.I + pw.c) % p.n_gblocks;
+        const long long j0 = (long long)K * IBLK + (long long)pw.t * TILE;
+        long long cnt = p.n_total - j0;
+        if (cnt > TILE) cnt = TILE;
+        const uint32_t bytes = (uint32_t)(cnt * sizeof(double4));
+        mbar_expect_tx(&full_bar[p_slot], bytes);
+        tma_bulk_g2s(tiles + (size_t)p_slot * TILE, p.pos_front_d + j0, bytes, &full_bar[p_slot]);
+        sym_advance<IBLK, TILE>(pw, p);
+        if (++p_slot == STAGES) p_slot = 0;
+    };
+    if (tid == 0) {
+        const int pre = ntiles < (STAGES - 1) ? ntiles : (STAGES - 1);
+        for (int k = 0; k < pre; ++k) issue_next();
+    }
+
+    double xi[R], yi[R], zi[R], mi[R];   // NEGATED positions, masses
+    double sx[R], sy[R], sz[R];
+    SymWalker w = w0;
+    bool new_row = true;
+    int c_slot = 0, e_slot = 0;
+    uint32_t c_parity = 0, e_parity = 0;
+    const int src_lane = (lane + 1) & 31;
+    const double e2 = p.eps2_d;
+
+    for (int k = 0; k < ntiles; ++k) {
+        if (new_row) {
+            new_row = false;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const long long il = (long long)w.I * IBLK + r * THREADS + tid;
+                double4 b = make_double4(1.0e150, 1.0e150, 1.0e150, 0.0);
+                if (il < p.n_local) b = p.pos_front_d[p.row0 + il];
+                xi[r] = -b.x; yi[r] = -b.y; zi[r] = -b.z; mi[r] = b.w;
+                sx[r] = 0.0; sy[r] = 0.0; sz[r] = 0.0;
+            }
+        }
+        if (tid == 0) {
+            const int kk = k + STAGES - 1;
+            if (kk < ntiles) {
+                if (kk >= STAGES) {
+                    mbar_wait(&empty_bar[e_slot], e_parity);
+                    if (++e_slot == STAGES) { e_slot = 0; e_parity ^= 1; }
+                }
+                issue_next();
+            }
+        }
+        const int s = c_slot;
+        mbar_wait(&full_bar[s], c_parity);
+        if (++c_slot == STAGES) { c_slot = 0; c_parity ^= 1; }
+        const double4* __restrict__ tile = tiles + (size_t)s * TILE;
+
+        const int Ig = p.gblock0 + w.I;
+        const int K = (Ig + w.c) % p.n_gblocks;
+        const long long j0 = (long long)K * IBLK + (long long)w.t * TILE;
+        long long cntl = p.n_total - j0;
+        const int jn = cntl > TILE ? TILE : (int)cntl;
+
+        if (w.c == 0) {
+            // diagonal block: ordered, j broadcast from shared memory, self pair masked by index
+            const int dj0 = (int)(j0 - ((long long)Ig * IBLK + tid));
+#pragma unroll 2
+            for (int j = 0; j < jn; ++j) {
+                const double4 b = tile[j];
+                const int dj = dj0 + j;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const double dx = b.x + xi[r], dy = b.y + yi[r], dz = b.z + zi[r];
+                    const double d2 = fma(dz, dz, fma(dy, dy, fma(dx, dx, e2)));
+                    double sc = mass_over_r3(b.w, d2);
+                    if (dj == r * THREADS) sc = 0.0;
+                    sx[r] = fma(dx, sc, sx[r]);
+                    sy[r] = fma(dy, sc, sy[r]);
+                    sz[r] = fma(dz, sc, sz[r]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+        } else {
+            double* jp = jpart + (size_t)warp * 3 * TILE;
+#pragma unroll 1
+            for (int c = 0; c < CHUNKS; ++c) {
+                const int jl = c * 32 + lane;
+                double4 bj = make_double4(-1.0e150, -1.0e150, -1.0e150, 0.0);
+                if (jl < jn) bj = tile[jl];
+                if (c == CHUNKS - 1) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_bar[s]);
+                }
+                double jx = 0.0, jy = 0.0, jz = 0.0;
+#pragma unroll UNROLL
+                for (int st = 0; st < 32; ++st) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const double dx = bj.x + xi[r], dy = bj.y + yi[r], dz = bj.z + zi[r];
+                        const double d2 = fma(dz, dz, fma(dy, dy, fma(dx, dx, e2)));
+                        const double w3 = mass_over_r3(1.0, d2);   // |d|^-3 (the multiply by 1.0 folds away)
+                        const double si = bj.w * w3, sj = mi[r] * w3;
+                        sx[r] = fma(dx, si, sx[r]);
+                        sy[r] = fma(dy, si, sy[r]);
+                        sz[r] = fma(dz, si, sz[r]);
+                        jx = fma(dx, sj, jx);
+                        jy = fma(dy, sj, jy);
+                        jz = fma(dz, sj, jz);
+                    }
+                    bj.x = __shfl_sync(0xffffffffu, bj.x, src_lane);
+                    bj.y = __shfl_sync(0xffffffffu, bj.y, src_lane);
+                    bj.z = __shfl_sync(0xffffffffu, bj.z, src_lane);
+                    bj.w = __shfl_sync(0xffffffffu, bj.w, src_lane);
+                    jx = __shfl_sync(0xffffffffu, jx, src_lane);
+                    jy = __shfl_sync(0xffffffffu, jy, src_lane);
+                    jz = __shfl_sync(0xffffffffu, jz, src_lane);
+                }
+                jp[0 * TILE + jl] = -jx;
+                jp[1 * TILE + jl] = -jy;
+                jp[2 * TILE + jl] = -jz;
+            }
+            __syncthreads();
+            for (int j = tid; j < jn; j += THREADS) {
+                double ax = 0.0, ay = 0.0, az = 0.0;
+#pragma unroll
+                for (int wv = 0; wv < NWARPS; ++wv) {
+                    ax += jpart[(wv * 3 + 0) * TILE + j];
+                    ay += jpart[(wv * 3 + 1) * TILE + j];
+                    az += jpart[(wv * 3 + 2) * TILE + j];
+                }
+                double* dst = p.acc64 + (j0 + j) * 4;
+                atomicAdd(dst + 0, ax);
+                atomicAdd(dst + 1, ay);
+                atomicAdd(dst + 2, az);
+            }
+            __syncthreads();   // jpart is single buffered
+        }
+
+        const int rowI = w.I;
+        sym_advance<IBLK, TILE>(w, p);
+        if (w.I != rowI || k == ntiles - 1) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const long long il = (long long)rowI * IBLK + r * THREADS + tid;
+                if (il < p.n_local) {
+                    double* dst = p.acc64 + (p.row0 + il) * 4;
+                    atomicAdd(dst + 0, sx[r]);
+                    atomicAdd(dst + 1, sy[r]);
+                    atomicAdd(dst + 2, sz[r]);
+                }
+            }
+            new_row = true;
+        }
+    }
+    if (p.clk && blockIdx.x == 0 && tid == 0) {
+        unsigned long long ns1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+        p.clk[0] = clock64() - clk0;
+        p.clk[1] = ns1 - ns0;
+    }
+}
+
+template <int THREADS, int TILE, int STAGES>
+constexpr size_t sym64_smem_bytes() {
+    return (size_t)STAGES * TILE * sizeof(double4) + 2 * STAGES * sizeof(uint64_t) + (size_t)(THREADS / 32) * 3 * TILE * sizeof(double);
+}
+
+// ------------------------------------------------------------------------------------------------
 // O(N) second half of a symmetric step: accumulator -> a, v', r' for this shard's rows, accumulator
 // cleared for the next step.  Same separately rounded stage-2 arithmetic as the fused epilogue
 // (finalize_body, np2.py:110-115), including the peer stores of the fused position exchange.
@@ -371,7 +598,9 @@ struct IntegrateParams {
     const double* acc_src[kMaxPeers + 1];
 };
 
+template <typename REAL>
 __global__ void sym_integrate_kernel(const IntegrateParams q) {
+    using V4 = typename Vec4<REAL>::type;
     const long long il = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (il >= q.sp.n_local) return;
     double sx, sy, sz;
@@ -387,8 +616,8 @@ __global__ void sym_integrate_kernel(const IntegrateParams q) {
             sx += s.x; sy += s.y; sz += s.z;
         }
     }
-    const float4 ri = reinterpret_cast<const float4*>(q.sp.pos_front)[q.sp.row0 + il];
-    finalize_body(q.sp, il, sx, sy, sz, ri, 0.f);
+    const V4 ri = reinterpret_cast<const V4*>(q.sp.pos_front)[q.sp.row0 + il];
+    finalize_body(q.sp, il, sx, sy, sz, ri, REAL(0));
 }
 
 }  // namespace gravb200

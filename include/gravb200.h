@@ -108,11 +108,11 @@ int gravb200_timings(gravb200_ctx* ctx, float* ms, int n);
  * [10]=exchange mode (GRAVB200_XCHG_*), [11]=variant id in use. */
 int gravb200_info(const gravb200_ctx* ctx, int64_t* info, int n);
 /* Force a kernel variant (tests / ncu A-B): variant < 0 restores the automatic choice.  Ids 0 .. count-1 are
- * the ordered sweeps (bit-reproducible), ids 100 + k, k < gravb200_sym_variant_count(), the symmetric fp32 sweeps
+ * the ordered sweeps (bit-reproducible), ids 100 + k, k < gravb200_sym_variant_count(dtype), the symmetric sweeps
  * (every unordered pair once, fp64 atomics: reproducible up to fp64 rounding of the cross-tile sum). */
 int gravb200_set_variant(gravb200_ctx* ctx, int variant);
 int gravb200_variant_count(int dtype);
-int gravb200_sym_variant_count(void);
+int gravb200_sym_variant_count(int dtype);
 const char* gravb200_variant_name(int dtype, int variant);
 
 /* Raw device pointers of the shard state (for peer access / torch interop in tests).
