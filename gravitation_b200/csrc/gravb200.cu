@@ -185,17 +185,17 @@ const std::vector<SymVariant>& variants_sym() {
     static const std::vector<SymVariant> v = {
         VSYM(256, 12, 512, 3, 2),   // 100 auto: large N on one GPU (IBLK 3072)
         VSYM(256, 8, 512, 3, 4),    // 101 auto: power-of-two IBLK 2048 (shards of several GPUs)
-        VSYM(256, 8, 256, 3, 2),    // 102 auto: medium N
+        VSYM(256, 8, 256, 3, 2),    // 102
         VSYM(256, 8, 512, 3, 2),    // 103
         VSYM(256, 8, 512, 3, 1),    // 104
         VSYM(256, 10, 512, 3, 2),   // 105
-        VSYM(128, 8, 256, 3, 2),    // 106
+        VSYM(128, 8, 256, 3, 2),    // 106 auto: 8192 <= N < 16384 (IBLK 1024)
         VSYM(256, 6, 512, 3, 2),    // 107
         VSYM(256, 12, 512, 3, 1),   // 108
         VSYM(256, 12, 512, 3, 4),   // 109
         VSYM(256, 14, 512, 3, 2),   // 110
         VSYM(256, 12, 256, 3, 2),   // 111
-        VSYM(256, 8, 256, 3, 4),    // 112
+        VSYM(256, 8, 256, 3, 4),    // 112 auto: 16384 <= N < 131072
         VSYM(256, 10, 256, 3, 2),   // 113
         VSYM(256, 16, 512, 3, 1),   // 114
     };
@@ -384,7 +384,8 @@ int pick_variant(gravb200_ctx* c) {
         int sv = -1;
         if (c->forced_variant >= kSymBase) sv = c->forced_variant - kSymBase;
         else if (c->forced_variant < 0 && c->n_total >= c->sym_min_n)
-            sv = c->dtype == GRAVB200_F32 ? (c->n_total >= 131072 ? 0 : 2) : (c->n_total >= 32768 ? 0 : 2);
+            sv = c->dtype == GRAVB200_F32 ? (c->n_total >= 131072 ? 0 : (c->n_total >= 16384 ? 12 : 6))
+                                          : (c->n_total >= 32768 ? 0 : 2);   // profiles/r01_sym*_variants_sweep.txt
         if (sv >= 0) return setup_sym(c, sv);
     } else if (c->world > 1 && c->peer_mode && c->acc64) {
         int sv = -1;
