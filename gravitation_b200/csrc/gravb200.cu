@@ -183,8 +183,8 @@ SymVariant make_sym(const char* name) {
 constexpr int kSymBase = 100;
 const std::vector<SymVariant>& variants_sym() {
     static const std::vector<SymVariant> v = {
-        VSYM(256, 12, 512, 3, 2),   // 100 auto: large N on one GPU (IBLK 3072)
-        VSYM(256, 8, 512, 3, 4),    // 101 auto: power-of-two IBLK 2048 (shards of several GPUs)
+        VSYM(256, 12, 512, 3, 2),   // 100 auto: N >= 65536 on one GPU (IBLK 3072)
+        VSYM(256, 8, 512, 3, 4),    // 101 auto: 16384 <= N < 65536; power-of-two IBLK 2048 (shards of several GPUs)
         VSYM(256, 8, 256, 3, 2),    // 102
         VSYM(256, 8, 512, 3, 2),    // 103
         VSYM(256, 8, 512, 3, 1),    // 104
@@ -195,9 +195,13 @@ const std::vector<SymVariant>& variants_sym() {
         VSYM(256, 12, 512, 3, 4),   // 109
         VSYM(256, 14, 512, 3, 2),   // 110
         VSYM(256, 12, 256, 3, 2),   // 111
-        VSYM(256, 8, 256, 3, 4),    // 112 auto: 16384 <= N < 131072
+        VSYM(256, 8, 256, 3, 4),    // 112
         VSYM(256, 10, 256, 3, 2),   // 113
         VSYM(256, 16, 512, 3, 1),   // 114
+        VSYM(384, 12, 256, 3, 1),   // 115  three warps per scheduler (<= 168 registers)
+        VSYM(384, 8, 256, 3, 2),    // 116
+        VSYM(384, 10, 256, 3, 1),   // 117
+        VSYM(384, 12, 128, 3, 1),   // 118
     };
     return v;
 }
@@ -384,8 +388,8 @@ int pick_variant(gravb200_ctx* c) {
         int sv = -1;
         if (c->forced_variant >= kSymBase) sv = c->forced_variant - kSymBase;
         else if (c->forced_variant < 0 && c->n_total >= c->sym_min_n)
-            sv = c->dtype == GRAVB200_F32 ? (c->n_total >= 131072 ? 0 : (c->n_total >= 16384 ? 12 : 6))
-                                          : (c->n_total >= 32768 ? 0 : 2);   // profiles/r01_sym*_variants_sweep.txt
+            sv = c->dtype == GRAVB200_F32 ? (c->n_total >= 65536 ? 0 : (c->n_total >= 16384 ? 1 : 6))
+                                          : (c->n_total >= 32768 ? 0 : 2);   // profiles/r01_sym*_variants_sweep*.txt
         if (sv >= 0) return setup_sym(c, sv);
     } else if (c->world > 1 && c->peer_mode && c->acc64) {
         int sv = -1;
@@ -1010,6 +1014,15 @@ int gravb200_timings(gravb200_ctx* c, float* ms, int n) {
         CU(cudaMemcpy(h, c->clk, sizeof(h), cudaMemcpyDeviceToHost));
         ms[3] = h[1] ? (float)((double)h[0] / (double)h[1] * 1e3) : -1.f;   // cycles/ns -> MHz
         if (n > 4) ms[4] = (float)((double)h[1] * 1e-6);   // lifetime of CTA 0 of the last sweep, ms
+#ifdef SYM_DEBUG
+        if (n > 6) {   // [2036..2046] divergence counters of SYM_DIVCHK, [2047] cycles spent in jbar waits
+            unsigned long long d[12];
+            CU(cudaMemcpy(d, c->clk + 2036, sizeof(d), cudaMemcpyDeviceToHost));
+            ms[5] = (float)d[10]; ms[6] = (float)((double)d[11] * 1e-6);
+            for (int i = 0; i < 10 && 7 + i < n; ++i) ms[7 + i] = (float)d[i];
+            CU(cudaMemset(c->clk + 2036, 0, sizeof(d)));
+        }
+#endif
     }
     return 0;
 }

@@ -91,6 +91,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// Non-blocking probe + a spin loop the compiler can see.  The blocking try_wait above may hand different
+// lanes of one warp their result at different times; the lanes then leave the (asm-internal) spin loop
+// separately and the warp stays diverged, which sends every following __shfl_sync down its slow path
+// (measured: 3-8x slower symmetric sweeps, profiles/r01_sym_divergence.md).  Warps that shuffle poll instead.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
+    while (!mbar_test(bar, parity)) {}
+}
+// Warp-uniform wait: every lane of a converged warp polls and the warp leaves the loop TOGETHER (vote).
+// No lane is ever left behind in a spin loop while the rest of its warp runs on: a warp split that way
+// (seen with a single producer lane polling the `empty` barrier) can stay split for the rest of the kernel.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    while (!__all_sync(0xffffffffu, mbar_test(bar, parity) ? 1 : 0)) {}
+}
 // global -> shared bulk copy, completion signalled on `bar` as transaction bytes
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
                                              uint64_t* bar) {
@@ -363,18 +389,19 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
             }
         }
         // producer step: refill the slot freed by tile k-1 with tile k+STAGES-1
-        if (tid == 0) {
+        if (tid < 32) {   // the whole first warp waits for the free slot (no lane is left behind polling), one lane issues
             const int kk = k + STAGES - 1;
             if (kk < ntiles) {
                 if (kk >= STAGES) {
-                    mbar_wait(&empty_bar[e_slot], e_parity);
+                    mbar_wait_warp(&empty_bar[e_slot], e_parity);
                     if (++e_slot == STAGES) { e_slot = 0; e_parity ^= 1; }
                 }
-                issue_next();
+                if (tid == 0) issue_next();
+                __syncwarp();
             }
         }
         const int s = c_slot;
-        mbar_wait(&full_bar[s], c_parity);
+        mbar_wait_warp(&full_bar[s], c_parity);
         if (++c_slot == STAGES) { c_slot = 0; c_parity ^= 1; }
         const V4* __restrict__ tile = tiles + (size_t)s * TILE;
 

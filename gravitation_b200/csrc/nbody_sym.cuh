@@ -28,6 +28,16 @@
 
 namespace gravb200 {
 
+#ifdef SYM_DEBUG   // dev builds: count warps that reach a point with fewer than 32 converged lanes
+#define SYM_DIVCHK(i)                                                                                      \
+    do {                                                                                                   \
+        const unsigned am_ = __activemask();                                                               \
+        if (p.clk && am_ != 0xffffffffu && (int)(threadIdx.x & 31) == __ffs(am_) - 1) atomicAdd(p.clk + 2036 + (i), 1ull); \
+    } while (0)
+#else
+#define SYM_DIVCHK(i) do {} while (0)
+#endif
+
 struct SymParams {
     const float4* pos_front;      // [n_pad] {x,y,z,m} of all bodies (fp32 kernel)
     const double4* pos_front_d;   // same, fp64 kernel
@@ -82,7 +92,7 @@ __device__ __forceinline__ void sym_advance(SymWalker& w, const SymParams& p) {
 
 // ------------------------------------------------------------------------------------------------
 // THREADS threads, R i-bodies per thread (even), TILE j-bodies per TMA stage (multiple of 32), STAGES.
-// Dynamic shared memory: tile ring | mbarriers | fp64 i-sums [3][R][THREADS] | j-partials [2][NWARPS][3][TILE].
+// Dynamic shared memory: tile ring | mbarriers (full, empty, jbar) | fp64 i-sums [3][R][THREADS] | j-partials [2][NWARPS][3][TILE].
 // ------------------------------------------------------------------------------------------------
 template <int THREADS, int R, int TILE, int STAGES, int UNROLL>
 __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p) {
@@ -96,7 +106,8 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
     float4* tiles = reinterpret_cast<float4*>(smem_raw);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * TILE * sizeof(float4));
     uint64_t* empty_bar = full_bar + STAGES;
-    double* ssum = reinterpret_cast<double*>(empty_bar + STAGES);                  // [3][R][THREADS]
+    uint64_t* jbar = empty_bar + STAGES;                                           // j-partials of a tile complete
+    double* ssum = reinterpret_cast<double*>(jbar + 1);                            // [3][R][THREADS]
     float* jpart = reinterpret_cast<float*>(ssum + (size_t)3 * R * THREADS);       // [2][NWARPS][3][TILE]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -108,6 +119,7 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NWARPS); }
+        mbar_init(jbar, NWARPS);
         mbar_fence_init();
     }
     __syncthreads();
@@ -179,7 +191,43 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
         }
     };
 
+    // j side of a finished symmetric tile: the warps' partials are combined in a fixed order and added to the
+    // global accumulator (one RED.ADD.F64 per body and component).  The combine is DEFERRED into the next
+    // tile: every warp arrives on `jbar` when its partials are written and goes on; the wait comes a whole
+    // ring round (32 steps) later, when all warps have long arrived, so no warp ever idles at a CTA barrier.
+    // jpart is double buffered: a buffer is rewritten two tiles later, after the wait that follows its combine.
+    bool jpend = false;
+    int jpend_n = 0, jpend_buf = 0;
+    long long jpend_j0 = 0;
+    uint32_t j_parity = 0;
+    auto combine_pending = [&]() {
+#ifdef SYM_DEBUG
+        const long long tw0 = clock64();
+#endif
+        mbar_wait_warp(jbar, j_parity);
+#ifdef SYM_DEBUG
+        if (p.clk && lane == 0) atomicAdd(p.clk + 2047, (unsigned long long)(clock64() - tw0));
+#endif
+        j_parity ^= 1;
+        const float* jb = jpart + (size_t)jpend_buf * NWARPS * 3 * TILE;
+        for (int j = tid; j < jpend_n; j += THREADS) {
+            double sx = 0.0, sy = 0.0, sz = 0.0;
+#pragma unroll
+            for (int wv = 0; wv < NWARPS; ++wv) {
+                sx += (double)jb[(wv * 3 + 0) * TILE + j];
+                sy += (double)jb[(wv * 3 + 1) * TILE + j];
+                sz += (double)jb[(wv * 3 + 2) * TILE + j];
+            }
+            double* dst = p.acc64 + (jpend_j0 + j) * 4;
+            atomicAdd(dst + 0, sx);
+            atomicAdd(dst + 1, sy);
+            atomicAdd(dst + 2, sz);
+        }
+        jpend = false;
+    };
+
     for (int k = 0; k < ntiles; ++k) {
+        SYM_DIVCHK(0);
         if (new_row) {
             new_row = false;
 #pragma unroll
@@ -195,18 +243,21 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
                 ssum[(2 * R + r) * THREADS + tid] = 0.0;
             }
         }
-        if (tid == 0) {
+        if (warp == 0) {   // producer: the whole warp waits for the free slot, one lane issues the bulk copy
             const int kk = k + STAGES - 1;
             if (kk < ntiles) {
                 if (kk >= STAGES) {
-                    mbar_wait(&empty_bar[e_slot], e_parity);
+                    mbar_wait_warp(&empty_bar[e_slot], e_parity);
                     if (++e_slot == STAGES) { e_slot = 0; e_parity ^= 1; }
                 }
-                issue_next();
+                if (lane == 0) issue_next();
+                __syncwarp();
             }
         }
+        SYM_DIVCHK(1);
         const int s = c_slot;
-        mbar_wait(&full_bar[s], c_parity);
+        mbar_wait_warp(&full_bar[s], c_parity);
+        SYM_DIVCHK(2);
         if (++c_slot == STAGES) { c_slot = 0; c_parity ^= 1; }
         const float4* __restrict__ tile = tiles + (size_t)s * TILE;
 
@@ -251,14 +302,28 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
 #pragma unroll 1
                 for (int j = 0; j < jn; ++j) ordered(tile[j], dj0 + j);
             }
+            SYM_DIVCHK(3);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (jpend) combine_pending();
+            SYM_DIVCHK(4);
         } else {
             // symmetric tile: ring over 32-body chunks
             float* jp = jpart + ((size_t)jbuf * NWARPS + warp) * 3 * TILE;
 #pragma unroll 1
             for (int c = 0; c < CHUNKS; ++c) {
                 const int jl = c * 32 + lane;
+                SYM_DIVCHK(10);
+#ifdef SYM_DEBUG
+                {   // log the first diverged chunk entries: CTA, warp, tile index in the CTA, chunk, active mask
+                    const unsigned am = __activemask();
+                    if (p.clk && am != 0xffffffffu && lane == __ffs(am) - 1) {
+                        const unsigned long long idx = atomicAdd(p.clk + 2035, 1ull);
+                        if (idx < 60) p.clk[1900 + idx] = ((unsigned long long)blockIdx.x << 52) | ((unsigned long long)warp << 48) |
+                                                           ((unsigned long long)k << 40) | ((unsigned long long)c << 32) | am;
+                    }
+                }
+#endif
                 // padding j-bodies sit at the opposite far corner from padding i-bodies, so d2 is never 0
                 float4 bj = make_float4(-1.0e30f, -1.0e30f, -1.0e30f, 0.f);
                 if (jl < jn) bj = tile[jl];
@@ -297,12 +362,15 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
                     jy.x = __shfl_sync(0xffffffffu, jy.x, src_lane); jy.y = __shfl_sync(0xffffffffu, jy.y, src_lane);
                     jz.x = __shfl_sync(0xffffffffu, jz.x, src_lane); jz.y = __shfl_sync(0xffffffffu, jz.y, src_lane);
                 }
+                SYM_DIVCHK(7);
                 // after 32 rotations every lane holds its own j-body again, with the sum over this warp's i-bodies
+                if (c == 0 && jpend) combine_pending();   // previous tile's j side (its buffer is the other one)
                 jp[0 * TILE + jl] = -(jx.x + jx.y);
                 jp[1 * TILE + jl] = -(jy.x + jy.y);
                 jp[2 * TILE + jl] = -(jz.x + jz.y);
             }
         }
+        SYM_DIVCHK(5);
         // i side: fp32 tile sums into this thread's fp64 sums
 #pragma unroll
         for (int q = 0; q < P; ++q) {
@@ -314,26 +382,14 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
             ssum[(2 * R + 2 * q + 1) * THREADS + tid] += (double)az[q].y;
         }
         if (w.c != 0) {
-            // j side: combine the warps in a fixed order, then one RED.ADD.F64 per body and component.
-            // jpart is double buffered, so one CTA barrier per symmetric tile is enough.
-            __syncthreads();
-            const float* jb = jpart + (size_t)jbuf * NWARPS * 3 * TILE;
-            for (int j = tid; j < jn; j += THREADS) {
-                double sx = 0.0, sy = 0.0, sz = 0.0;
-#pragma unroll
-                for (int wv = 0; wv < NWARPS; ++wv) {
-                    sx += (double)jb[(wv * 3 + 0) * TILE + j];
-                    sy += (double)jb[(wv * 3 + 1) * TILE + j];
-                    sz += (double)jb[(wv * 3 + 2) * TILE + j];
-                }
-                double* dst = p.acc64 + (j0 + j) * 4;
-                atomicAdd(dst + 0, sx);
-                atomicAdd(dst + 1, sy);
-                atomicAdd(dst + 2, sz);
-            }
+            // j side: this warp's partials are in shared memory; the combine happens in the next tile
+            __syncwarp();
+            if (lane == 0) mbar_arrive(jbar);
+            jpend = true; jpend_n = jn; jpend_j0 = j0; jpend_buf = jbuf;
             jbuf ^= 1;
         }
 
+        SYM_DIVCHK(6);
         const int rowI = w.I;
         sym_advance<IBLK, TILE>(w, p);
         if (w.I != rowI || k == ntiles - 1) {
@@ -344,17 +400,18 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
             new_row = true;
         }
     }
+    if (jpend) combine_pending();
     if (p.clk && tid == 0) {
         unsigned long long ns1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
         if (blockIdx.x == 0) { p.clk[0] = clock64() - clk0; p.clk[1] = ns1 - ns0; }
-        if (blockIdx.x < 1022) { p.clk[2 + 2 * blockIdx.x] = ns0; p.clk[3 + 2 * blockIdx.x] = ns1; }
+        if (blockIdx.x < 1016) { p.clk[2 + 2 * blockIdx.x] = ns0; p.clk[3 + 2 * blockIdx.x] = ns1; }
     }
 }
 
 template <int THREADS, int R, int TILE, int STAGES>
 constexpr size_t sym_smem_bytes() {
-    return (size_t)STAGES * TILE * sizeof(float4) + 2 * STAGES * sizeof(uint64_t) + (size_t)3 * R * THREADS * sizeof(double) +
+    return (size_t)STAGES * TILE * sizeof(float4) + (2 * STAGES + 1) * sizeof(uint64_t) + (size_t)3 * R * THREADS * sizeof(double) +
            (size_t)2 * (THREADS / 32) * 3 * TILE * sizeof(float);
 }
 
@@ -457,18 +514,19 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
                 sx[r] = 0.0; sy[r] = 0.0; sz[r] = 0.0;
             }
         }
-        if (tid == 0) {
+        if (warp == 0) {   // producer: the whole warp waits for the free slot, one lane issues the bulk copy
             const int kk = k + STAGES - 1;
             if (kk < ntiles) {
                 if (kk >= STAGES) {
-                    mbar_wait(&empty_bar[e_slot], e_parity);
+                    mbar_wait_warp(&empty_bar[e_slot], e_parity);
                     if (++e_slot == STAGES) { e_slot = 0; e_parity ^= 1; }
                 }
-                issue_next();
+                if (lane == 0) issue_next();
+                __syncwarp();
             }
         }
         const int s = c_slot;
-        mbar_wait(&full_bar[s], c_parity);
+        mbar_wait_warp(&full_bar[s], c_parity);
         if (++c_slot == STAGES) { c_slot = 0; c_parity ^= 1; }
         const double4* __restrict__ tile = tiles + (size_t)s * TILE;
 

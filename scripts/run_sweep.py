@@ -15,5 +15,5 @@ best = 1e30
 for _ in range(reps):
     sh.stage1(); sh.stage2()
     t = sh.timings(); best = min(best, t['sweep_ms'])
-print(json.dumps(dict(n=n, dtype=dtype, variant=_shim.variant_names(dtype)[variant] if variant >= 0 else 'auto', best_ms=best,
+print(json.dumps(dict(n=n, dtype=dtype, variant=('auto' if variant < 0 else _shim.sym_variant_names(dtype)[variant - _shim.SYM_BASE] if variant >= _shim.SYM_BASE else _shim.variant_names(dtype)[variant]), best_ms=best,
     tera_inter_s=n * (n - 1) / best / 1e9, sm_mhz=t['sm_mhz'], info=sh.info())))

@@ -227,6 +227,25 @@ def test_analyze_accepts_good_logs_and_rejects_bad_ones():
 			analyze.parse_log(bad)
 
 
+def test_analyze_summary_rate_and_fraction_of_peak(tmp_path):
+	"""dtype and GPU count as axes, interactions/s and %-of-peak columns"""
+	import json
+	from gravitation_b200.cli import analyze
+	runs = analyze.parse_log(_fake_log())
+	runs[0]['meta']['simulation'].update(scenario_param = {'stars_len': 16, 'dtype': 'float64'}, threads = 2)
+	rows = analyze.summarize(runs)
+	assert len(rows) == 1 and rows[0]['dtype'] == 'float64' and rows[0]['threads'] == 2 and rows[0]['bodies'] == 16
+	rate = 16 * 15 / 101e-9 # best of the three fake steps is 101 ns
+	assert rows[0]['g_interactions_per_s'] == pytest.approx(rate / 1e9)
+	assert rows[0]['fraction_of_peak'] == pytest.approx(rate * 20 / (2 * 37.22e12))
+	assert analyze.summarize(runs, peak_tflops = 10.0)[0]['fraction_of_peak'] == pytest.approx(rate * 20 / (2 * 10e12))
+	log = tmp_path / 'b.log'
+	log.write_text(_fake_log() + _fake_log(steps = 2))
+	analyze.main(['-l', str(log), '-o', str(tmp_path / 'b.json'), '--summary'])
+	assert len(json.loads((tmp_path / 'b.json.summary.json').read_text())) == 2
+	assert 'G interactions/s' in analyze.format_summary(rows)
+
+
 def test_benchmark_size_range_matches_reference_rule():
 	from gravitation_b200.cli.benchmark import size_range, worker_command
 	assert size_range(2, 4) == [4, 6, 8, 12, 16] and size_range(3, 3) == [8]
