@@ -51,6 +51,7 @@ _SIGNATURES = [
 	('gravb200_sync', ctypes.c_int, [_c_ctx]),
 	('gravb200_download', ctypes.c_int, [_c_ctx, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
 	('gravb200_shard', ctypes.c_int, [_c_ctx, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
+	('gravb200_partition', ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
 	('gravb200_timings', ctypes.c_int, [_c_ctx, ctypes.POINTER(ctypes.c_float), ctypes.c_int]),
 	('gravb200_info', ctypes.c_int, [_c_ctx, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
 	('gravb200_set_variant', ctypes.c_int, [_c_ctx, ctypes.c_int]),
@@ -148,6 +149,17 @@ def variant_names(dtype = 'float32'):
 	lib = load()
 	d = _DTYPES[dtype]
 	return [lib.gravb200_variant_name(d, i).decode() for i in range(lib.gravb200_variant_count(d))]
+
+
+def partition(n, world, dtype = 'float32'):
+	"""[(row0, n_local)] of every shard — the partition gravb200_ctx_create applies (needs no device)"""
+	lib = load()
+	out = []
+	for rank in range(world):
+		row0, n_local = ctypes.c_int64(), ctypes.c_int64()
+		_check(lib.gravb200_partition(int(n), _DTYPES[dtype], int(world), rank, ctypes.byref(row0), ctypes.byref(n_local)))
+		out.append((row0.value, n_local.value))
+	return out
 
 
 def sym_variant_names(dtype = 'float32'):

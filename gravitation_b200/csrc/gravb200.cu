@@ -234,6 +234,21 @@ const std::vector<SymVariant>& variants_sym64() {
 }
 const std::vector<SymVariant>& variants_sym_of(int dtype) { return dtype == GRAVB200_F32 ? variants_sym() : variants_sym64(); }
 
+// Rows per shard (contiguous slices, the last one short).  ceil(n / world), rounded up to
+// whole body-blocks of the fastest symmetric sweep of `dtype` (variant 100: IBLK 3072 fp32, 1536 fp64) when
+// that costs the fullest shard less than 1.5 % extra rows — then several GPUs run the same variant as one GPU
+// (N = 2^20 fp32 on 8 GPUs: 43 blocks = 132 096 rows instead of 131 072, +0.8 %, for a 6 % faster sweep).
+// Small universes keep the plain partition (they run the ordered sweep or the power-of-two variant 101).
+constexpr int64_t kSymShardMinN = 32768;
+int64_t shard_chunk(int64_t n_total, int world, int dtype) {
+    const int64_t plain = (n_total + world - 1) / world;
+    if (world <= 1 || n_total < kSymShardMinN) return plain;
+    const SymVariant& v = variants_sym_of(dtype)[0];
+    const int64_t iblk = (int64_t)v.threads * v.r;
+    const int64_t aligned = (plain + iblk - 1) / iblk * iblk;
+    return (aligned - plain) * 1000 < plain * 15 ? aligned : plain;
+}
+
 // ---------------------------------------------------------------------------------------------
 // O(N) helper kernels: layout conversion between the reference's (N,3)+(N,) host arrays
 // (np2.py:63-66) and the device float4/double4 state.
@@ -394,7 +409,11 @@ int pick_variant(gravb200_ctx* c) {
     } else if (c->world > 1 && c->peer_mode && c->acc64) {
         int sv = -1;
         if (c->forced_variant >= kSymBase) sv = c->forced_variant - kSymBase;
-        else if (c->forced_variant < 0 && c->n_total >= 4 * c->sym_min_n) sv = 1;
+        else if (c->forced_variant < 0 && c->n_total >= kSymShardMinN) {
+            // the one-GPU variant when the shards are whole blocks of it (shard_chunk), else the power-of-two one
+            const SymVariant& v0 = variants_sym_of(c->dtype)[0];
+            sv = c->chunk % ((long long)v0.threads * v0.r) == 0 ? 0 : 1;
+        }
         if (sv >= 0) {
             const SymVariant& v = variants_sym_of(c->dtype)[sv];
             const long long iblk = (long long)v.threads * v.r;
@@ -786,7 +805,7 @@ int gravb200_ctx_create(int64_t n_total, int dtype, int device, int rank, int wo
     c->rank = rank;
     c->world = world;
     c->n_total = n_total;
-    c->chunk = (n_total + world - 1) / world;
+    c->chunk = shard_chunk(n_total, world, dtype);
     c->n_pad = c->chunk * world;
     c->row0 = std::min<int64_t>((int64_t)rank * c->chunk, n_total);
     c->n_local = std::max<int64_t>(0, std::min<int64_t>(c->chunk, n_total - c->row0));
@@ -993,6 +1012,16 @@ int gravb200_download(gravb200_ctx* c, void* r, void* v, void* a) {
     if (!c->uploaded) return fail(GRAVB200_EINVAL, "no state uploaded");
     CU(cudaSetDevice(c->device));
     return c->dtype == GRAVB200_F32 ? download_impl<float, float4>(c, r, v, a) : download_impl<double, double4>(c, r, v, a);
+}
+
+int gravb200_partition(int64_t n_total, int dtype, int world, int rank, int64_t* row0, int64_t* n_local) {
+    if (n_total < 0 || world < 1 || rank < 0 || rank >= world) return fail(GRAVB200_EINVAL, "bad partition arguments");
+    if (dtype != GRAVB200_F32 && dtype != GRAVB200_F64) return fail(GRAVB200_EINVAL, "dtype must be GRAVB200_F32 or GRAVB200_F64");
+    const int64_t chunk = shard_chunk(n_total, world, dtype);
+    const int64_t r0 = std::min<int64_t>((int64_t)rank * chunk, n_total);
+    if (row0) *row0 = r0;
+    if (n_local) *n_local = std::max<int64_t>(0, std::min<int64_t>(chunk, n_total - r0));
+    return 0;
 }
 
 int gravb200_shard(const gravb200_ctx* c, int64_t* row0, int64_t* n_local) {

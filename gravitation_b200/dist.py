@@ -6,21 +6,19 @@ libgravb200 on its own stream (NCCL all-gather over NVLink).  torch.distributed 
 rendezvous (unique-id broadcast, barriers, max-over-ranks timing) and for gathering per-shard rows
 (velocities, accelerations) onto every rank when a caller asks for them.
 
-Row partition = SURVEY.md section 8e: contiguous slices of ceil(N / P) rows, the last one short."""
+Row partition = SURVEY.md section 8e: contiguous slices of ceil(N / P) rows (rounded up to whole body-blocks
+of the symmetric sweep for large N), the last one short; the library is the single source of it."""
 
 import os
 
 import numpy as np
 
 
-def row_partition(n, world):
-	"""[(row0, n_local)] per rank — must agree with gravb200_ctx_create (csrc/gravb200.cu)"""
-	chunk = (n + world - 1) // world
-	out = []
-	for rank in range(world):
-		row0 = min(rank * chunk, n)
-		out.append((row0, max(0, min(chunk, n - row0))))
-	return out
+def row_partition(n, world, dtype = 'float32'):
+	"""[(row0, n_local)] per rank, asked from the library so that it IS the partition gravb200_ctx_create
+	applies (csrc/gravb200.cu shard_chunk: ceil(n / world) rows, block-aligned for large universes)"""
+	from . import _shim
+	return _shim.partition(n, world, dtype)
 
 
 def env_world():
@@ -92,12 +90,13 @@ def connect_peers(shard):
 	return mode
 
 
-def gather_rows(local_rows, n):
+def gather_rows(local_rows, n, dtype = None):
 	"""all ranks contribute their (n_local, k) slice and receive the assembled (n, k) array"""
 	import torch
 	import torch.distributed as dist
 	world = dist.get_world_size()
-	chunk = (n + world - 1) // world
+	parts = row_partition(n, world, dtype or ('float64' if local_rows.dtype == np.float64 else 'float32'))
+	chunk = max(cnt for _, cnt in parts)
 	k = local_rows.shape[1]
 	send = np.zeros((chunk, k), dtype = local_rows.dtype)
 	send[:local_rows.shape[0], :] = local_rows
@@ -107,7 +106,7 @@ def gather_rows(local_rows, n):
 		t = t.cuda()
 	out = [torch.empty_like(t) for _ in range(world)]
 	dist.all_gather(out, t)
-	full = torch.cat(out, dim = 0)[:n]
+	full = torch.cat([o[:cnt] for o, (_, cnt) in zip(out, parts)], dim = 0)
 	return full.cpu().numpy()
 
 

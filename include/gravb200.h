@@ -96,6 +96,10 @@ int gravb200_sync(gravb200_ctx* ctx);
  * (world == 1: all bodies).  Any pointer may be NULL. */
 int gravb200_download(gravb200_ctx* ctx, void* r, void* v, void* a);
 int gravb200_shard(const gravb200_ctx* ctx, int64_t* row0, int64_t* n_local);
+/* The row partition gravb200_ctx_create applies, without a context or a device (hosts that lay out their
+ * mirrors before creating shards): contiguous slices of ceil(n_total / world) rows — rounded up to whole
+ * body-blocks of the symmetric sweep when that costs under 1.5 % — the last slice short or empty. */
+int gravb200_partition(int64_t n_total, int dtype, int world, int rank, int64_t* row0, int64_t* n_local);
 
 /* Device-side timings (cudaEvent): ms[0] = last stage1 sweep kernel, ms[1] = last exchange,
  * ms[2] = total of the last gravb200_steps() call, ms[3] = SM clock (MHz) that CTA 0 of the last sweep

@@ -186,14 +186,22 @@ def test_product_code_never_touches_the_oracle():
 
 def test_row_partition_covers_all_rows():
 	from gravitation_b200.dist import row_partition
-	for n, world in ((1 << 20, 8), (5, 8), (1000, 3), (7, 1)):
-		parts = row_partition(n, world)
-		assert len(parts) == world and sum(c for _, c in parts) == n
-		pos = 0
-		for row0, cnt in parts:
-			if cnt:
-				assert row0 == pos
-			pos += cnt
+	for dtype in ('float32', 'float64'):
+		for n, world in ((1 << 20, 8), (1 << 20, 2), (1 << 18, 8), (1 << 24, 8), (5, 8), (1000, 3), (7, 1), (40000, 2), (100003, 4)):
+			parts = row_partition(n, world, dtype)
+			assert len(parts) == world and sum(c for _, c in parts) == n
+			pos = 0
+			for row0, cnt in parts:
+				if cnt:
+					assert row0 == pos
+				pos += cnt
+			# never more than 1.5 % above the even share (load balance), and no empty shard once n >= world
+			assert max(c for _, c in parts) <= -(-n // world) * 1.015 + 1
+			assert n < world or min(c for _, c in parts) > 0
+	# the headline configuration: whole 3072-row blocks of the one-GPU symmetric variant on every full shard
+	parts = row_partition(1 << 20, 8, 'float32')
+	assert parts[0][1] == 43 * 3072 and all(r0 % 3072 == 0 for r0, _ in parts)
+	assert row_partition(1 << 18, 8, 'float64')[0][1] == 1 << 15 # +3 % would be too much: plain partition
 
 
 # ---- worker protocol / analyze (cli/worker.py:115-245, cli/analyze.py:47-108) ----------------------
