@@ -136,7 +136,7 @@ def reference_arm(args):
 		'e2e': {'value': res['g_inter_s'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
 		'gpu_launches': 0,
 		}
-	print(json.dumps(line), flush = True)
+	_emit(line)
 	return 0
 
 
@@ -336,7 +336,7 @@ def own_arm(args):
 		line['cpu_baseline'] = cpu
 	if gpu_ref is not None:
 		line['reference_gpu_kernel'] = gpu_ref
-	print(json.dumps(line), flush = True)
+	_emit(line)
 	return 0
 
 
@@ -347,6 +347,34 @@ def _shutdown():
 			tdist.destroy_process_group()
 	except Exception:
 		pass
+
+
+class _StdoutGuard:
+	"""The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to
+	stdout when NCCL_DEBUG is set on the box), so file descriptor 1 points at stderr while the bench runs
+	and is restored for the result line."""
+
+	def __enter__(self):
+		sys.stdout.flush()
+		self._saved = os.dup(1)
+		os.dup2(2, 1)
+		return self
+
+	def __exit__(self, *exc):
+		sys.stdout.flush()
+		os.dup2(self._saved, 1)
+		os.close(self._saved)
+
+
+def _emit(line):
+	"""print the result line on the REAL stdout (see _StdoutGuard)"""
+	sys.stdout.flush()
+	fd = getattr(_emit, 'fd', None)
+	payload = (json.dumps(line) + '\n').encode()
+	if fd is None:
+		sys.stdout.write(payload.decode()); sys.stdout.flush()
+	else:
+		os.write(fd, payload)
 
 
 def main():
@@ -362,11 +390,16 @@ def main():
 	args = ap.parse_args()
 	if args.warmup < 3:
 		args.warmup = 3
-	if args.impl == 'reference':
-		return reference_arm(args)
-	rc = own_arm(args)
-	_shutdown()
-	return rc
+	with _StdoutGuard() as guard:
+		_emit.fd = guard._saved
+		try:
+			if args.impl == 'reference':
+				return reference_arm(args)
+			rc = own_arm(args)
+			_shutdown()
+			return rc
+		finally:
+			_emit.fd = None
 
 
 if __name__ == '__main__':

@@ -259,3 +259,23 @@ def test_benchmark_size_range_matches_reference_rule():
 	assert size_range(2, 4) == [4, 6, 8, 12, 16] and size_range(3, 3) == [8]
 	cmd = worker_command('b200', 4096, 2, 10, 0)
 	assert cmd[1:3] == ['-m', 'gravitation_b200.cli.worker'] and '{"stars_len": 4096}' in cmd and cmd[-1] == '2'
+
+
+# ---- bench.py contract: exactly one JSON line on stdout, whatever libraries print ------------------
+
+def test_bench_reference_arm_prints_one_json_line():
+	"""`bench.py --impl reference` (the CPU arm; the one place outside tests that may execute oracle/): one
+	JSON line on stdout with the contract's keys; everything else (library banners, warnings) is on stderr"""
+	import json, subprocess, sys
+	root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+	if not os.path.isfile(os.path.join(root, 'oracle', '_ref', 'lib4.so')) and not os.path.isfile(os.path.join(root, 'oracle', 'liboracle.so')):
+		pytest.skip('oracle not built')
+	out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '3'],
+		capture_output = True, text = True, timeout = 600)
+	assert out.returncode == 0, out.stderr[-2000:]
+	lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+	assert len(lines) == 1
+	line = json.loads(lines[0])
+	assert line['impl'] == 'reference' and line['unit'] == 'G interactions/s' and line['higher_is_better'] is True
+	assert line['value'] > 0 and line['e2e']['value'] == line['value'] and line['e2e']['h2d_bytes_per_step'] == 0
+	assert line['cpu_baseline']['kind'] in ('reference', 'port') and line['cpu_baseline']['cores'] >= 1
