@@ -323,6 +323,9 @@ struct gravb200_ctx {
     long long sym_min_n = 8192;    // automatic choice: symmetric sweep from this N on
     int sym_variant = 0, sym_blocks = 0, sym_gblocks = 0;
     long long sym_total = 0;
+    // gravb200_steps on one GPU, launch-bound sizes: kGraphSteps steps captured once per front-buffer parity
+    cudaGraphExec_t step_graph[2] = {nullptr, nullptr};
+    int64_t step_graph_kernels = 0;   // kernel nodes in one of them
 };
 
 namespace {
@@ -392,7 +395,21 @@ int setup_sym(gravb200_ctx* c, int sv) {
     return 0;
 }
 
+// CUDA graph of kGraphSteps (even: the front buffer is the same before and after) full steps.  Kernel
+// arguments depend only on the front-buffer parity, the variant and G/T/eps, so a graph stays valid until
+// one of those changes (pick_variant, upload).
+constexpr int kGraphSteps = 8;
+constexpr int64_t kGraphMaxN = 32768;   // above, a step takes > 0.3 ms and launch latency is noise
+
+void graph_invalidate(gravb200_ctx* c) {
+    for (auto& g : c->step_graph) {
+        if (g) cudaGraphExecDestroy(g);
+        g = nullptr;
+    }
+}
+
 int pick_variant(gravb200_ctx* c) {
+    graph_invalidate(c);
     c->use_sym = false;
     // symmetric sweep: forced (ids >= kSymBase) or automatic once there are enough body-blocks.  Several
     // shards need the peer-store exchange (the owner of a row reads the other shards' partial sums over
@@ -581,6 +598,37 @@ int peer_barrier(gravb200_ctx* c) {
     exchange_barrier_kernel<<<1, 32, 0, c->stream>>>(b);
     CU(cudaGetLastError());
     c->launches++;
+    return 0;
+}
+
+int step_graph_for(gravb200_ctx* c, cudaGraphExec_t* out) {
+    const int f = c->front;
+    if (!c->step_graph[f]) {
+        const int64_t launches0 = c->launches;
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = 0;
+        for (int s = 0; s < kGraphSteps && !rc; ++s) {
+            rc = launch_sweep(c, 1);
+            c->front ^= 1;
+        }
+        const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+        c->step_graph_kernels = c->launches - launches0;
+        c->launches = launches0;   // nothing ran yet
+        c->front = f;
+        if (rc || e != cudaSuccess) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            return rc ? rc : fail(GRAVB200_ECUDA, "stream capture of the step graph failed: %s", cudaGetErrorString(e));
+        }
+        const cudaError_t ei = cudaGraphInstantiate(&c->step_graph[f], g, 0);
+        cudaGraphDestroy(g);
+        if (ei != cudaSuccess) {
+            c->step_graph[f] = nullptr;
+            return fail(GRAVB200_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+        }
+    }
+    *out = c->step_graph[f];
     return 0;
 }
 
@@ -863,6 +911,7 @@ int gravb200_ctx_destroy(gravb200_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    graph_invalidate(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (int b = 0; b < 2; ++b) {
         if (c->pos[b]) cudaFree(c->pos[b]);
@@ -897,6 +946,7 @@ int gravb200_upload(gravb200_ctx* c, const void* r, const void* v, const void* m
     if (!r || !v || !m) return fail(GRAVB200_EINVAL, "r, v and m are required");
     if (eps < 0) return fail(GRAVB200_EINVAL, "eps must be >= 0");
     CU(cudaSetDevice(c->device));
+    if (c->G != G || c->T != T || c->eps != eps) graph_invalidate(c);
     c->G = G; c->T = T; c->eps = eps;
     c->pending = false;
     int rc = c->dtype == GRAVB200_F32 ? upload_impl<float, float4>(c, r, v, m) : upload_impl<double, double4>(c, r, v, m);
@@ -986,7 +1036,18 @@ int gravb200_steps(gravb200_ctx* c, int k) {
     CU(cudaSetDevice(c->device));
     c->pending = false;
     CU(cudaEventRecord(c->ev[0], c->stream));
-    for (int s = 0; s < k; ++s) {
+    int s = 0;
+    if (c->world == 1 && c->n_total <= kGraphMaxN && c->n_local > 0) {
+        // launch-bound sizes: whole groups of kGraphSteps steps go out as one graph launch each
+        for (; k - s >= kGraphSteps; s += kGraphSteps) {
+            cudaGraphExec_t ex = nullptr;
+            int rc = step_graph_for(c, &ex);
+            if (rc) return rc;
+            CU(cudaGraphLaunch(ex, c->stream));
+            c->launches += c->step_graph_kernels;
+        }
+    }
+    for (; s < k; ++s) {
         int rc = launch_sweep(c, 1);
         if (rc) return rc;
         rc = exchange(c);

@@ -87,7 +87,8 @@ int gravb200_group_end(void);
 int gravb200_peer_export(gravb200_ctx* ctx, void* blob);
 int gravb200_peer_connect(gravb200_ctx* ctx, const void* blobs);
 int gravb200_set_exchange_mode(gravb200_ctx* ctx, int mode);
-/* k fused steps without host involvement (launch-bound small N: captured in a CUDA graph). */
+/* k fused steps without host involvement.  One GPU and N <= 32768 (launch-bound): groups of 8 steps are
+ * captured once in a CUDA graph and replayed, the remainder is launched step by step. */
 int gravb200_steps(gravb200_ctx* ctx, int k);
 int gravb200_sync(gravb200_ctx* ctx);
 

@@ -186,6 +186,40 @@ def test_steps_equals_repeated_stage_calls_and_is_deterministic(dtype, oracle, g
 			assert np.array_equal(x, y) # bit-identical: fixed-order combination of split i-blocks
 
 
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('n,variant', ((700, -1), (2048 + 77, 1), (9000, -1)))
+def test_graph_replayed_steps_equal_single_steps(n, variant, dtype, oracle, gpu):
+	"""steps(k) replays groups of 8 steps from a CUDA graph on launch-bound sizes (plus single launches for the
+	remainder); the state must equal k stage1()+stage2() calls — bit for bit with the ordered sweeps, to fp64
+	rounding of the accumulator with the symmetric one (n = 9000) — also after a re-upload with another T"""
+	r, v, m, G, T = oracle.uniform_universe(n, 33, dtype)
+	for t_step, k in ((T, 19), (T * 0.5, 8)):
+		outs = []
+		for mode in ('stages', 'steps'):
+			sh = gpu.Shard(n, dtype)
+			sh.upload(r, v, m, G, T)
+			if variant >= 0:
+				sh.set_variant(variant)
+			if t_step != T:
+				sh.steps(9) # builds the graph for the first time step ...
+				sh.upload(r, v, m, G, t_step) # ... which the new T must invalidate
+			launches0 = sh.info()['launches']
+			if mode == 'stages':
+				for _ in range(k):
+					sh.stage1(); sh.stage2()
+			else:
+				sh.steps(k)
+			assert sh.info()['launches'] - launches0 == k * (2 if sh.info()['variant'] >= gpu.SYM_BASE else 1)
+			outs.append(sh.download(a = True))
+			symmetric = sh.info()['variant'] >= gpu.SYM_BASE
+			sh.close()
+		for x, y in zip(*outs):
+			if symmetric:
+				assert traj_err(y, x.astype(np.float64)) <= (1e-6 if dtype == 'float32' else 1e-13)
+			else:
+				assert np.array_equal(x, y)
+
+
 def test_upload_positions_only(oracle, gpu):
 	n = 500
 	r, v, m, G, T = oracle.uniform_universe(n, 2, 'float32')
