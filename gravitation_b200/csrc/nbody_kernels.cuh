@@ -78,23 +78,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// Non-blocking probe + a spin loop the compiler can see.  The blocking try_wait above may hand different
-// lanes of one warp their result at different times; the lanes then leave the (asm-internal) spin loop
-// separately and the warp stays diverged, which sends every following __shfl_sync down its slow path
-// (measured: 3-8x slower symmetric sweeps, profiles/r01_sym_divergence.md).  Warps that shuffle poll instead.
+// Waiting on an mbarrier: a non-blocking probe in a spin loop the compiler can see, left on a warp vote.
+// The first version spun on the blocking `mbarrier.try_wait` inside one asm block (branches hidden from the
+// compiler): lanes of one warp could get their result at different times, left the loop separately and the
+// warp stayed split, which sends every following __shfl_sync down its slow path (3-8x slower symmetric
+// sweeps, profiles/r01_sym_divergence.md).
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -107,9 +95,6 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
-    while (!mbar_test(bar, parity)) {}
 }
 // Warp-uniform wait: every lane of a converged warp polls and the warp leaves the loop TOGETHER (vote).
 // No lane is ever left behind in a spin loop while the rest of its warp runs on: a warp split that way

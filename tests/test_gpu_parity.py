@@ -472,6 +472,37 @@ def test_symmetric_sweep_parity_and_reproducibility(n, dtype, oracle, gpu):
 	assert oracle.max_rel_err(outs[1][2], aa) <= (3e-7 if dtype == 'float32' else 1e-12) # run to run, per body
 
 
+def test_symmetric_sweep_random_sizes_and_variants(oracle, gpu):
+	"""fuzz (scripts/sym_fuzz.py, fixed seed): random N x random symmetric variant move the CTA ranges over row
+	ends, diagonal blocks and ragged tiles — where the deferred j-combine and the ring barriers could go wrong.
+	All rows against the float64 oracle, stage 2 bit-exact, steps(3) == 3 x (stage1, stage2)"""
+	rng = np.random.default_rng(77)
+	for case in range(9):
+		dtype = DTYPES[case % 2]
+		names = gpu.sym_variant_names(dtype)
+		n = int(rng.integers(1100, 45000))
+		vid = gpu.SYM_BASE + int(rng.integers(0, len(names)))
+		r, v, m, G, T = oracle.uniform_universe(n, 900 + case, dtype)
+		sh = gpu.Shard(n, dtype)
+		sh.upload(r, v, m, G, T)
+		sh.set_variant(vid)
+		sh.stage1(); sh.stage2()
+		r1, v1, a1 = sh.download(a = True)
+		what = '%s n=%d %s' % (dtype, n, names[vid - gpu.SYM_BASE])
+		assert oracle.max_rel_err(a1, oracle.stage1_f64(r, m, G)) <= TOL_ACC[dtype], what
+		r_ref, v_ref = r.copy(), v.copy()
+		oracle.stage2(r_ref, v_ref, a1, T)
+		assert np.array_equal(r1, r_ref) and np.array_equal(v1, v_ref), what
+		for _ in range(2):
+			sh.stage1(); sh.stage2()
+		r3, v3, _ = sh.download()
+		sh.upload(r, v, m, G, T)
+		sh.steps(3)
+		r3b, v3b, _ = sh.download()
+		sh.close()
+		assert traj_err(r3b, r3.astype(np.float64)) <= (1e-6 if dtype == 'float32' else 1e-13), what
+
+
 def test_symmetric_sweep_on_two_gpus(oracle, gpu):
 	"""several shards: every shard sweeps its block rows symmetrically into a full-size accumulator, the
 	owner of a row adds all shards' partial sums over NVLink inside the integrate kernel"""
