@@ -22,6 +22,12 @@
 // added into a global fp64 accumulator with RED.ADD.F64; `integrate_kernel` (O(N)) turns the accumulator
 // into a, v', r'.  The fp64 sums of fp32 tile partials are exact unless the partials of one body span
 // more than 2^29 in magnitude, so results are reproducible up to that rounding, not by construction.
+//
+// Synchronisation: there is no CTA-wide barrier in the sweep loop.  j-tiles arrive through the TMA/mbarrier
+// ring; the j-side combine of a tile is deferred into the next tile behind an mbarrier (combine_pending);
+// every wait is warp-uniform (mbar_wait_warp) and the producer is the whole first warp, because a warp that
+// shuffles must never split (profiles/r01_sym_divergence.md).  -DSYM_DEBUG builds count diverged warps and
+// the cycles spent waiting (scripts/dbg/sym_dbg2.py).
 #pragma once
 
 #include "nbody_kernels.cuh"
