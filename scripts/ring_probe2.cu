@@ -6,6 +6,8 @@
 //   MODE 2  j-body read from shared memory (LDS.128, rotating index, prefetched one step ahead); 6 SHFL
 //   MODE 3  MODE 2 + the halves of the packed partials are summed before travelling (3 FADD + 3 SHFL)
 //   MODE 4  MODE 1 with scalar FFMA for the j-side accumulation
+//   MODE 5  MODE 1 with the six accumulates of a pair written zig-zag (consecutive ones share one operand);
+//           ptxas reorders them anyway: no gain
 #include <cstdio>
 #include <cuda_runtime.h>
 __device__ __forceinline__ float rsq(float x){float y; asm("rsqrt.approx.ftz.f32 %0, %1;":"=f"(y):"f"(x)); return y;}
@@ -32,7 +34,7 @@ __global__ void __launch_bounds__(THREADS, 1) ring(const float4* __restrict__ po
 #pragma unroll UNR
     for (int s = 0; s < steps; ++s) {
         float4 nx;
-        if (MODE == 1 || MODE == 4) { nx.x = SH(bj.x); nx.y = SH(bj.y); nx.z = SH(bj.z); nx.w = SH(bj.w); }
+        if (MODE == 1 || MODE == 4 || MODE == 5) { nx.x = SH(bj.x); nx.y = SH(bj.y); nx.z = SH(bj.z); nx.w = SH(bj.w); }
         if (MODE == 2 || MODE == 3) { nx = tile[wbase + ((lane + s + 2) & 31)]; }
 #pragma unroll
         for (int q = 0; q < P; ++q) {
@@ -46,11 +48,20 @@ __global__ void __launch_bounds__(THREADS, 1) ring(const float4* __restrict__ po
             const float2 ri2 = __fmul2_rn(ri, ri);
             const float2 ri3 = __fmul2_rn(ri2, ri);
             const float2 si = __fmul2_rn(make_float2(bj.w, bj.w), ri3);
-            ax[q] = __ffma2_rn(dx, si, ax[q]);
-            ay[q] = __ffma2_rn(dy, si, ay[q]);
-            az[q] = __ffma2_rn(dz, si, az[q]);
             const float2 sj = __fmul2_rn(mi[q], ri3);
-            if (MODE == 4) {
+            if (MODE != 5) {
+                ax[q] = __ffma2_rn(dx, si, ax[q]);
+                ay[q] = __ffma2_rn(dy, si, ay[q]);
+                az[q] = __ffma2_rn(dz, si, az[q]);
+            }
+            if (MODE == 5) {   // zig-zag: consecutive accumulates share one operand (dx | sj | dy | si | dz)
+                ax[q] = __ffma2_rn(dx, si, ax[q]);
+                jx = __ffma2_rn(dx, sj, jx);
+                jy = __ffma2_rn(dy, sj, jy);
+                ay[q] = __ffma2_rn(dy, si, ay[q]);
+                az[q] = __ffma2_rn(dz, si, az[q]);
+                jz = __ffma2_rn(dz, sj, jz);
+            } else if (MODE == 4) {
                 jx.x = fmaf(dx.x, sj.x, jx.x); jx.y = fmaf(dx.y, sj.y, jx.y);
                 jy.x = fmaf(dy.x, sj.x, jy.x); jy.y = fmaf(dy.y, sj.y, jy.y);
                 jz.x = fmaf(dz.x, sj.x, jz.x); jz.y = fmaf(dz.y, sj.y, jz.y);
@@ -61,7 +72,7 @@ __global__ void __launch_bounds__(THREADS, 1) ring(const float4* __restrict__ po
             }
         }
         if (MODE == 0) { bj.x = SH(bj.x); bj.y = SH(bj.y); bj.z = SH(bj.z); bj.w = SH(bj.w); }
-        else if (MODE == 1 || MODE == 4) bj = nx;
+        else if (MODE == 1 || MODE == 4 || MODE == 5) bj = nx;
         else { bj = bn; bn = nx; }
         if (MODE == 3) {
             const float tx = jx.x + jx.y, ty = jy.x + jy.y, tz = jz.x + jz.y;
@@ -99,6 +110,8 @@ int main() {
     for (int i = 0; i < 8192; ++i) h[i] = make_float4(i * 1.37f, i * 0.91f + 3.f, i * 2.11f - 7.f, 1.f + (i % 7));
     cudaMemcpy(pos, h, 8192 * 16, cudaMemcpyHostToDevice);
     run<12, 256, 0, 2>(pos, out, cyc, sms);
+    run<12, 256, 5, 2>(pos, out, cyc, sms);
+    run<12, 256, 5, 1>(pos, out, cyc, sms);
     run<12, 256, 1, 2>(pos, out, cyc, sms);
     run<12, 256, 2, 2>(pos, out, cyc, sms);
     run<12, 256, 3, 2>(pos, out, cyc, sms);

@@ -37,6 +37,11 @@ def oracle():
 
 @pytest.fixture(scope = 'session')
 def shim():
+	"""the ctypes binding; builds libgravb200.so first if this checkout has not been built yet
+	(nvcc cross-compiles for sm_100a without a GPU; normally __graft_entry__.build() did that already)"""
 	from gravitation_b200 import _shim
+	if not os.path.isfile(_shim.LIB_PATH):
+		import subprocess
+		subprocess.run(['make', '-C', os.path.join(ROOT, 'gravitation_b200', 'csrc'), 'all'], check = True, capture_output = True)
 	_shim.load()
 	return _shim

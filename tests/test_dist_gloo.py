@@ -38,7 +38,7 @@ def _worker(rank, world, port, n, out_dir):
 
 
 @pytest.mark.parametrize('n', (10, 7, 1))
-def test_two_rank_gloo_plumbing(n, tmp_path):
+def test_two_rank_gloo_plumbing(n, tmp_path, shim):
 	import torch.multiprocessing as mp
 	port = _free_port()
 	mp.spawn(_worker, args = (2, port, n, str(tmp_path)), nprocs = 2, join = True)

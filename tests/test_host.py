@@ -184,7 +184,7 @@ def test_product_code_never_touches_the_oracle():
 				assert not re.search(r'^\s*(from|import)\s+oracle|liboracle|oracle/_ref', src, re.M), fn
 
 
-def test_row_partition_covers_all_rows():
+def test_row_partition_covers_all_rows(shim):
 	from gravitation_b200.dist import row_partition
 	for dtype in ('float32', 'float64'):
 		for n, world in ((1 << 20, 8), (1 << 20, 2), (1 << 18, 8), (1 << 24, 8), (5, 8), (1000, 3), (7, 1), (40000, 2), (100003, 4)):
