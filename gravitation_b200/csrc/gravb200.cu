@@ -656,6 +656,16 @@ int exchange(gravb200_ctx* c) {
     return 0;
 }
 
+// An upload replaces the state a pending stage1 was computed from: the step is dropped.  On several shards
+// the symmetric sweep has left partial sums in the accumulator (one shard: the integrate kernel cleared
+// it; several: the clear belongs to the exchange that will not happen).
+int drop_pending(gravb200_ctx* c) {
+    if (c->pending && c->use_sym && c->world > 1 && c->acc64)
+        CU(cudaMemsetAsync(c->acc64, 0, (size_t)c->n_pad * 4 * sizeof(double), c->stream));
+    c->pending = false;
+    return 0;
+}
+
 template <typename REAL, typename V4>
 int upload_impl(gravb200_ctx* c, const void* r, const void* v, const void* m) {
     const long long n = c->n_total;
@@ -948,7 +958,8 @@ int gravb200_upload(gravb200_ctx* c, const void* r, const void* v, const void* m
     CU(cudaSetDevice(c->device));
     if (c->G != G || c->T != T || c->eps != eps) graph_invalidate(c);
     c->G = G; c->T = T; c->eps = eps;
-    c->pending = false;
+    int rc0 = drop_pending(c);
+    if (rc0) return rc0;
     int rc = c->dtype == GRAVB200_F32 ? upload_impl<float, float4>(c, r, v, m) : upload_impl<double, double4>(c, r, v, m);
     if (rc) return rc;
     // masses travel in .w of both buffers: copy front -> back once so the epilogue's w is consistent
@@ -968,8 +979,9 @@ int gravb200_upload_positions(gravb200_ctx* c, const void* r) {
     if (!c || !r) return fail(GRAVB200_EINVAL, "ctx / r is NULL");
     if (!c->uploaded) return fail(GRAVB200_EINVAL, "gravb200_upload must come first");
     CU(cudaSetDevice(c->device));
-    c->pending = false;
-    int rc = c->dtype == GRAVB200_F32 ? upload_impl<float, float4>(c, r, nullptr, nullptr)
+    int rc = drop_pending(c);
+    if (rc) return rc;
+    rc = c->dtype == GRAVB200_F32 ? upload_impl<float, float4>(c, r, nullptr, nullptr)
                                       : upload_impl<double, double4>(c, r, nullptr, nullptr);
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
@@ -1034,7 +1046,8 @@ int gravb200_steps(gravb200_ctx* c, int k) {
     if (!c->uploaded) return fail(GRAVB200_EINVAL, "no state uploaded");
     if (k < 0) return fail(GRAVB200_EINVAL, "k < 0");
     CU(cudaSetDevice(c->device));
-    c->pending = false;
+    int rc0 = drop_pending(c);
+    if (rc0) return rc0;
     CU(cudaEventRecord(c->ev[0], c->stream));
     int s = 0;
     if (c->world == 1 && c->n_total <= kGraphMaxN && c->n_local > 0) {
