@@ -234,19 +234,32 @@ const std::vector<SymVariant>& variants_sym64() {
 }
 const std::vector<SymVariant>& variants_sym_of(int dtype) { return dtype == GRAVB200_F32 ? variants_sym() : variants_sym64(); }
 
-// Rows per shard (contiguous slices, the last one short).  ceil(n / world), rounded up to
-// whole body-blocks of the fastest symmetric sweep of `dtype` (variant 100: IBLK 3072 fp32, 1536 fp64) when
-// that costs the fullest shard less than 1.5 % extra rows — then several GPUs run the same variant as one GPU
-// (N = 2^20 fp32 on 8 GPUs: 43 blocks = 132 096 rows instead of 131 072, +0.8 %, for a 6 % faster sweep).
-// Small universes keep the plain partition (they run the ordered sweep or the power-of-two variant 101).
+// Rows per shard (contiguous slices, the last one short).  Several shards can run the
+// symmetric sweep only on whole body-blocks of a variant, so the shard size is chosen by predicted step time:
+// ceil(n / world) rounded up to blocks of symmetric variant 100 (IBLK 3072 fp32 / 1536 fp64) or 101 (IBLK
+// 2048) at their measured rates, against the plain ceil(n / world) with the ordered sweep
+// (profiles/r01_sym_variants_sweep2.txt, r01_sym64_variants_sweep.txt, one B200, large N).  N = 2^20 fp32 on
+// 8 GPUs: 43 blocks = 132 096 rows instead of 131 072 (+0.8 %) for the 6 % faster variant; an arbitrary N
+// trades a few per cent of imbalance for not falling back to the ordered sweep (-28 %).  The last shard must
+// keep at least one row.  Small universes keep the plain partition (ordered sweep or variant 101).
 constexpr int64_t kSymShardMinN = 32768;
 int64_t shard_chunk(int64_t n_total, int world, int dtype) {
     const int64_t plain = (n_total + world - 1) / world;
     if (world <= 1 || n_total < kSymShardMinN) return plain;
-    const SymVariant& v = variants_sym_of(dtype)[0];
-    const int64_t iblk = (int64_t)v.threads * v.r;
-    const int64_t aligned = (plain + iblk - 1) / iblk * iblk;
-    return (aligned - plain) * 1000 < plain * 15 ? aligned : plain;
+    const double rate_sym[2] = {dtype == GRAVB200_F32 ? 3.65 : 1.46, dtype == GRAVB200_F32 ? 3.44 : 1.40};   // T inter/s
+    const double rate_ordered = dtype == GRAVB200_F32 ? 2.62 : 1.01;
+    int64_t best = plain;
+    double best_cost = (plain % ((int64_t)variants_sym_of(dtype)[1].threads * variants_sym_of(dtype)[1].r) == 0)
+                           ? (double)plain / rate_sym[1] : (double)plain / rate_ordered;
+    for (int o = 0; o < 2; ++o) {
+        const SymVariant& v = variants_sym_of(dtype)[o];
+        const int64_t iblk = (int64_t)v.threads * v.r;
+        const int64_t aligned = (plain + iblk - 1) / iblk * iblk;
+        if ((int64_t)(world - 1) * aligned >= n_total) continue;   // would leave the last shard empty
+        const double cost = (double)aligned / rate_sym[o];
+        if (cost < 0.98 * best_cost) { best_cost = cost; best = aligned; }   // 2 % margin: the rates are estimates
+    }
+    return best;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -428,6 +441,7 @@ int pick_variant(gravb200_ctx* c) {
         if (c->forced_variant >= kSymBase) sv = c->forced_variant - kSymBase;
         else if (c->forced_variant < 0 && c->n_total >= kSymShardMinN) {
             // the one-GPU variant when the shards are whole blocks of it (shard_chunk), else the power-of-two one
+            // (N = 2^20 on 3 shards is whole blocks of both: the faster one wins)
             const SymVariant& v0 = variants_sym_of(c->dtype)[0];
             sv = c->chunk % ((long long)v0.threads * v0.r) == 0 ? 0 : 1;
         }

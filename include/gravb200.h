@@ -98,8 +98,10 @@ int gravb200_sync(gravb200_ctx* ctx);
 int gravb200_download(gravb200_ctx* ctx, void* r, void* v, void* a);
 int gravb200_shard(const gravb200_ctx* ctx, int64_t* row0, int64_t* n_local);
 /* The row partition gravb200_ctx_create applies, without a context or a device (hosts that lay out their
- * mirrors before creating shards): contiguous slices of ceil(n_total / world) rows — rounded up to whole
- * body-blocks of the symmetric sweep when that costs under 1.5 % — the last slice short or empty. */
+ * mirrors before creating shards): contiguous slices of ceil(n_total / world) rows — for n_total >= 32768
+ * rounded up to whole body-blocks of a symmetric sweep variant when the predicted step time is shorter
+ * than with the ordered sweep on the plain partition — the last slice short (never empty for
+ * n_total >= 32768; empty slices only when n_total < world). */
 int gravb200_partition(int64_t n_total, int dtype, int world, int rank, int64_t* row0, int64_t* n_local);
 
 /* Device-side timings (cudaEvent): ms[0] = last stage1 sweep kernel, ms[1] = last exchange,
