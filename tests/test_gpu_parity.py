@@ -530,7 +530,7 @@ def test_symmetric_sweep_on_two_gpus(oracle, gpu):
 @pytest.mark.parametrize('dtype,n', (('float32', 1 << 18), ('float64', 1 << 17)))
 def test_symmetric_sweep_on_block_aligned_shards(dtype, n, oracle, gpu):
 	"""large universes on several GPUs: the shards are whole body-blocks of the one-GPU symmetric variant
-	(gravb200_partition rounds ceil(N/P) up when that costs < 1.5 %), so every GPU runs variant 100; the last
+	(gravb200_partition rounds ceil(N/P) up when the predicted step time is shorter), so every GPU runs variant 100; the last
 	shard is short.  Sampled rows against the oracle, then two more steps against a single GPU."""
 	if gpu.device_count() < 2:
 		pytest.skip('needs 2 GPUs')
