@@ -87,7 +87,7 @@ struct SymWalker {
 };
 
 template <int IBLK, int TILE>
-__device__ __forceinline__ void sym_advance(SymWalker& w, const SymParams& p) {
+__host__ __device__ __forceinline__ void sym_advance(SymWalker& w, const SymParams& p) {   // host: tests/native/sym_schedule_check.cu
     const int Ig = p.gblock0 + w.I;
     const int K = (Ig + w.c) % p.n_gblocks;
     if (++w.t == sym_tiles_in_block(p.n_total, IBLK, TILE, K)) {

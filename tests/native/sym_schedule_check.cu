@@ -1,0 +1,112 @@
+// Host-side check of the symmetric sweep's work decomposition (csrc/nbody_sym.cuh), compiled and run by
+// tests/test_host.py::test_symmetric_schedule_visits_every_block_pair_once — no GPU needed.
+//
+// For many (N, IBLK, TILE, shard count) it replays what the kernels do with the geometry helpers
+// (sym_ncols, sym_tiles_in_block, sym_row_tiles, sym_advance) and checks the properties the physics needs:
+//   1. every unordered pair of body-blocks {A, B} (A == B included) is visited exactly once over all shards,
+//   2. sym_row_tiles (the host's row_start table) equals the number of tiles the walker steps through,
+//   3. the walker enumerates (row, column, tile) in exactly the order of the nested loops and ends at the
+//      end of the last local row, whatever flat offset a CTA starts from (binary search + walk, as in the kernel),
+//   4. the j-tiles of a row cover its column blocks completely (ragged last block included),
+//   5. block rows carry equal work up to one column block (load balance across shards).
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../../gravitation_b200/csrc/nbody_sym.cuh"
+
+using namespace gravb200;
+
+static long long fails = 0;
+#define CHECK(cond, ...) do { if (!(cond)) { if (fails < 20) { printf("FAIL %s:%d: ", __FILE__, __LINE__); printf(__VA_ARGS__); printf("\n"); } ++fails; } } while (0)
+
+template <int IBLK, int TILE>
+void check(long long n, int world, long long chunk) {
+    const int Bt = (int)((n + IBLK - 1) / IBLK);
+    std::vector<int> visited((size_t)Bt * Bt, 0);
+    long long min_row = -1, max_row = -1;
+    for (int rank = 0; rank < world; ++rank) {
+        const long long row0 = std::min<long long>((long long)rank * chunk, n);
+        const long long n_local = std::max<long long>(0, std::min<long long>(chunk, n - row0));
+        if (n_local == 0) continue;
+        const int nib = (int)((n_local + IBLK - 1) / IBLK);
+        SymParams p;
+        p.n_total = n; p.row0 = row0; p.n_local = n_local; p.n_iblocks = nib; p.n_gblocks = Bt; p.gblock0 = (int)(row0 / IBLK);
+        std::vector<long long> rs((size_t)nib + 1, 0);
+        for (int i = 0; i < nib; ++i) rs[i + 1] = rs[i] + sym_row_tiles(n, IBLK, TILE, Bt, p.gblock0 + i);
+        // nested-loop enumeration, the reference order
+        std::vector<SymWalker> order;
+        for (int I = 0; I < nib; ++I) {
+            const int Ig = p.gblock0 + I;
+            const int nc = sym_ncols(Bt, Ig);
+            long long tiles = 0, bodies = 0;
+            for (int c = 0; c < nc; ++c) {
+                const int K = (Ig + c) % Bt;
+                ++visited[(size_t)std::min(Ig, K) * Bt + std::max(Ig, K)];
+                CHECK(c == 0 || K != Ig, "row %d revisits its diagonal block", Ig);
+                const int tb = sym_tiles_in_block(n, IBLK, TILE, K);
+                for (int t = 0; t < tb; ++t) {
+                    order.push_back({I, c, t});
+                    const long long j0 = (long long)K * IBLK + (long long)t * TILE;
+                    bodies += std::min<long long>(TILE, n - j0);
+                    CHECK(j0 < n, "tile starts past the last body");
+                }
+                tiles += tb;
+                const long long in_block = std::min<long long>(IBLK, n - (long long)K * IBLK);
+                CHECK(in_block > 0, "empty column block");
+            }
+            CHECK(tiles == rs[I + 1] - rs[I], "sym_row_tiles %lld != walked %lld (n=%lld Ig=%d)", rs[I + 1] - rs[I], tiles, n, Ig);
+            long long expect = 0;
+            for (int c = 0; c < nc; ++c) expect += std::min<long long>(IBLK, n - (long long)((Ig + c) % Bt) * IBLK);
+            CHECK(bodies == expect, "tiles of row %d cover %lld bodies, blocks hold %lld", Ig, bodies, expect);
+            if (min_row < 0 || nc < min_row) min_row = nc;
+            if (nc > max_row) max_row = nc;
+        }
+        CHECK((long long)order.size() == rs[nib], "flat size");
+        // the walker from the start, and from every 7th flat offset located the kernel's way
+        for (long long lo = 0; lo < rs[nib]; lo += (lo == 0 ? 1 : 7)) {
+            int a = 0, b = nib;
+            while (b - a > 1) { const int m = (a + b) >> 1; if (rs[m] <= lo) a = m; else b = m; }
+            SymWalker w{a, 0, 0};
+            long long rem = lo - rs[a];
+            for (;;) {
+                const int tb = sym_tiles_in_block(n, IBLK, TILE, (p.gblock0 + a + w.c) % Bt);
+                if (rem < tb) break;
+                rem -= tb; ++w.c;
+            }
+            w.t = (int)rem;
+            const long long span = lo == 0 ? rs[nib] : std::min<long long>(rs[nib] - lo, 40);
+            for (long long k = 0; k < span; ++k) {
+                const SymWalker& e = order[(size_t)(lo + k)];
+                CHECK(w.I == e.I && w.c == e.c && w.t == e.t, "walker (%d,%d,%d) != (%d,%d,%d) at %lld (n=%lld)", w.I, w.c, w.t, e.I, e.c, e.t, lo + k, n);
+                sym_advance<IBLK, TILE>(w, p);
+            }
+            if (lo == 0) CHECK(w.I == nib && w.c == 0 && w.t == 0, "walker ends at (%d,%d,%d), not at row %d", w.I, w.c, w.t, nib);
+        }
+    }
+    for (int A = 0; A < Bt; ++A)
+        for (int B = A; B < Bt; ++B)
+            CHECK(visited[(size_t)A * Bt + B] == 1, "block pair (%d,%d) of %d visited %d times (n=%lld iblk=%d world=%d)", A, B, Bt, visited[(size_t)A * Bt + B], n, IBLK, world);
+    CHECK(max_row - min_row <= 1, "block rows differ by %lld column blocks", max_row - min_row);
+}
+
+template <int IBLK, int TILE>
+void sweep(long long& cases) {
+    const long long sizes[] = {1, 2, TILE - 1, TILE, TILE + 1, IBLK - 1, IBLK, IBLK + 1, 2LL * IBLK, 2LL * IBLK + 5, 3LL * IBLK - 1, 5LL * IBLK + TILE,
+                               8LL * IBLK, 9LL * IBLK - 7, 17LL * IBLK + 33, 40000, 65536, 100003, 262144, 1048576};
+    for (long long n : sizes) {
+        check<IBLK, TILE>(n, 1, n); ++cases;
+        for (int world : {2, 3, 4, 8}) {
+            const long long plain = (n + world - 1) / world;
+            const long long chunk = (plain + IBLK - 1) / IBLK * IBLK;   // shards are whole blocks (gravb200_partition)
+            check<IBLK, TILE>(n, world, chunk); ++cases;
+        }
+    }
+}
+
+int main() {
+    long long cases = 0;
+    sweep<3072, 512>(cases); sweep<3072, 256>(cases); sweep<2048, 512>(cases); sweep<2048, 256>(cases);
+    sweep<1024, 256>(cases); sweep<1536, 256>(cases); sweep<1536, 128>(cases); sweep<1024, 128>(cases);
+    printf("%s: %lld cases, %lld failed checks\n", fails ? "FAILED" : "OK", cases, fails);
+    return fails ? 1 : 0;
+}

@@ -285,3 +285,22 @@ def test_bench_reference_arm_prints_one_json_line():
 	assert line['impl'] == 'reference' and line['unit'] == 'G interactions/s' and line['higher_is_better'] is True
 	assert line['value'] > 0 and line['e2e']['value'] == line['value'] and line['e2e']['h2d_bytes_per_step'] == 0
 	assert line['cpu_baseline']['kind'] in ('reference', 'port') and line['cpu_baseline']['cores'] >= 1
+
+
+# ---- the symmetric sweep's work decomposition, replayed on the host (csrc/nbody_sym.cuh) ------------
+
+def test_symmetric_schedule_visits_every_block_pair_once(tmp_path):
+	"""tests/native/sym_schedule_check.cu includes the kernel header and replays its geometry helpers and its
+	tile walker on the CPU: every unordered pair of body-blocks exactly once over all shards, row_start table
+	== walked tiles, walker order == nested loops from any flat offset, ragged last block covered, block
+	rows balanced to one column block.  nvcc only cross-compiles; nothing runs on a device."""
+	import shutil, subprocess
+	nvcc = shutil.which('nvcc') or ('/usr/local/cuda/bin/nvcc' if os.path.isfile('/usr/local/cuda/bin/nvcc') else None)
+	if nvcc is None:
+		pytest.skip('nvcc not available')
+	exe = str(tmp_path / 'sym_schedule_check')
+	build = subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-O1', '-std=c++17', '-o', exe,
+		os.path.join(ROOT, 'tests', 'native', 'sym_schedule_check.cu')], capture_output = True, text = True)
+	assert build.returncode == 0, build.stderr[-3000:]
+	run = subprocess.run([exe], capture_output = True, text = True, timeout = 300)
+	assert run.returncode == 0 and run.stdout.strip().splitlines()[-1].startswith('OK:'), run.stdout[-3000:]
