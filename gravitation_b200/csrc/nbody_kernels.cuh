@@ -141,11 +141,11 @@ __device__ __forceinline__ double4 ld_cg_d4(const double4* p) {   // L2-coherent
 }
 
 // stream-K partition helpers: CTA c owns flat tiles [lo(c), lo(c+1))
-__device__ __forceinline__ long long sk_lo(long long total, long long c, long long S) {
+__host__ __device__ __forceinline__ long long sk_lo(long long total, long long c, long long S) {
     return total * c / S;
 }
 // the CTA that owns flat tile t
-__device__ __forceinline__ long long sk_owner(long long total, long long t, long long S) {
+__host__ __device__ __forceinline__ long long sk_owner(long long total, long long t, long long S) {
     return ((t + 1) * S - 1) / total;
 }
 

@@ -1,4 +1,4 @@
-// Host-side check of the symmetric sweep's work decomposition (csrc/nbody_sym.cuh), compiled and run by
+// Host-side check of the work decomposition of the sweeps (csrc/nbody_sym.cuh, csrc/nbody_kernels.cuh), compiled and run by
 // tests/test_host.py::test_symmetric_schedule_visits_every_block_pair_once — no GPU needed.
 //
 // For many (N, IBLK, TILE, shard count) it replays what the kernels do with the geometry helpers
@@ -103,8 +103,32 @@ void sweep(long long& cases) {
     }
 }
 
+// stream-K partition of the ordered sweep (csrc/nbody_kernels.cuh): CTA c owns flat tiles [sk_lo(c), sk_lo(c+1));
+// the ranges tile [0, total) without gap or overlap, differ by at most one tile, and sk_owner inverts sk_lo
+void check_stream_k(long long& cases) {
+    const long long totals[] = {1, 2, 3, 7, 147, 148, 149, 295, 296, 297, 1000, 4096, 65536, 1048576, 4194304 + 17, (1LL << 31) + 5, 3LL << 33};
+    const long long grids[] = {1, 2, 3, 37, 148, 296, 592};
+    for (long long total : totals)
+        for (long long S : grids) {
+            ++cases;
+            CHECK(sk_lo(total, 0, S) == 0 && sk_lo(total, S, S) == total, "ends (total=%lld S=%lld)", total, S);
+            long long lo_min = total, lo_max = 0;
+            for (long long c = 0; c < S; ++c) {
+                const long long lo = sk_lo(total, c, S), hi = sk_lo(total, c + 1, S);
+                CHECK(lo <= hi, "range order");
+                lo_min = std::min(lo_min, hi - lo); lo_max = std::max(lo_max, hi - lo);
+                if (hi > lo) {
+                    CHECK(sk_owner(total, lo, S) == c, "owner of first tile %lld of CTA %lld is %lld (total=%lld S=%lld)", lo, c, sk_owner(total, lo, S), total, S);
+                    CHECK(sk_owner(total, hi - 1, S) == c, "owner of last tile %lld of CTA %lld is %lld (total=%lld S=%lld)", hi - 1, c, sk_owner(total, hi - 1, S), total, S);
+                }
+            }
+            CHECK(lo_max - lo_min <= 1, "ranges differ by %lld tiles (total=%lld S=%lld)", lo_max - lo_min, total, S);
+        }
+}
+
 int main() {
     long long cases = 0;
+    check_stream_k(cases);
     sweep<3072, 512>(cases); sweep<3072, 256>(cases); sweep<2048, 512>(cases); sweep<2048, 256>(cases);
     sweep<1024, 256>(cases); sweep<1536, 256>(cases); sweep<1536, 128>(cases); sweep<1024, 128>(cases);
     printf("%s: %lld cases, %lld failed checks\n", fails ? "FAILED" : "OK", cases, fails);

@@ -304,3 +304,29 @@ def test_symmetric_schedule_visits_every_block_pair_once(tmp_path):
 	assert build.returncode == 0, build.stderr[-3000:]
 	run = subprocess.run([exe], capture_output = True, text = True, timeout = 300)
 	assert run.returncode == 0 and run.stdout.strip().splitlines()[-1].startswith('OK:'), run.stdout[-3000:]
+
+
+def test_row_partition_properties_hypothesis(shim):
+	"""random (n, world, dtype): slices are contiguous, cover [0, n), all but the last are equal, the last is
+	never empty for n >= world, and a non-plain shard size is a whole number of symmetric-sweep blocks"""
+	from hypothesis import given, settings, strategies as st
+
+	@settings(max_examples = 300, deadline = None)
+	@given(n = st.integers(min_value = 0, max_value = 1 << 25), world = st.integers(min_value = 1, max_value = 8),
+		dtype = st.sampled_from(('float32', 'float64')))
+	def check(n, world, dtype):
+		parts = shim.partition(n, world, dtype)
+		assert len(parts) == world and sum(c for _, c in parts) == n
+		chunk = parts[0][1]
+		pos = 0
+		for row0, cnt in parts:
+			assert row0 == min(pos, n) and 0 <= cnt <= chunk
+			pos += chunk
+		plain = -(-n // world)
+		if chunk != plain:
+			assert n >= 32768 and world > 1 and chunk > plain
+			assert chunk % (3072 if dtype == 'float32' else 1536) == 0 or chunk % 2048 == 0
+			assert parts[-1][1] > 0 and chunk <= plain * 1.39 + 1
+		if n >= world:
+			assert all(cnt > 0 for _, cnt in parts) or chunk == plain
+	check()
