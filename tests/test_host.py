@@ -330,3 +330,46 @@ def test_row_partition_properties_hypothesis(shim):
 		if n >= world:
 			assert all(cnt > 0 for _, cnt in parts) or chunk == plain
 	check()
+
+
+# ---- static evidence from the compiled library: what the default kernels are made of ---------------
+
+def test_sass_of_the_default_kernels(shim):
+	"""cuobjdump -sass of libgravb200.so (sm_100a): the automatic large-N variants stage j-tiles with TMA bulk
+	copies (UBLKCP) behind mbarriers probed without blocking (SYNCS.PHASECHK, no TRYWAIT), compute with packed
+	FFMA2 / DFMA and MUFU.RSQ, keep everything in registers (no local-memory spills), and the symmetric fp32
+	sweep has no CTA-wide barrier after its prologue (one BAR for the mbarrier initialisation)"""
+	import collections, shutil, subprocess
+	tool = shutil.which('cuobjdump') or ('/usr/local/cuda/bin/cuobjdump' if os.path.isfile('/usr/local/cuda/bin/cuobjdump') else None)
+	if tool is None:
+		pytest.skip('cuobjdump not available')
+	text = subprocess.run([tool, '-sass', shim.LIB_PATH], capture_output = True, text = True, check = True).stdout
+	assert 'sm_100a' in text
+	funcs, cur = {}, None
+	for line in text.splitlines():
+		m = re.search(r'Function : (\S+)', line)
+		if m:
+			cur = m.group(1); funcs[cur] = []
+			continue
+		m = re.match(r'\s+/\*[0-9a-f]{4,}\*/\s+(.*?);', line)
+		if cur is not None and m:
+			funcs[cur].append(re.sub(r'^@!?U?P\d+\s+', '', m.group(1)))
+	def census(key):
+		names = [f for f in funcs if key in f]
+		assert len(names) == 1, (key, names)
+		ins = funcs[names[0]]
+		return collections.Counter(i.split()[0].split('.')[0] for i in ins), ins
+	for key, must, bars in (
+		('sym_sweep_kernelILi256ELi12ELi512ELi3ELi2E', ('UBLKCP', 'FFMA2', 'FADD2', 'FMUL2', 'MUFU', 'SHFL', 'REDG', 'VOTE'), 1), # fp32 symmetric, variant 100
+		('sym_sweep_kernel_f64ILi256ELi6ELi256ELi3ELi1ELi2E', ('UBLKCP', 'DFMA', 'MUFU', 'SHFL', 'REDG', 'VOTE'), 3), # fp64 symmetric, variant 100
+		('sweep_kernelIfLi256ELi8ELi512ELi3ELi1ELi1ELi4ELi1E', ('UBLKCP', 'FFMA2', 'FADD2', 'FMUL2', 'MUFU', 'VOTE'), None), # fp32 ordered, variant 0
+		('sweep_kernelIdLi256ELi2ELi256ELi3ELi2ELi0ELi4ELi0E', ('UBLKCP', 'DFMA', 'MUFU', 'VOTE'), None), # fp64 ordered, variant 0
+		):
+		ops, ins = census(key)
+		for op in must:
+			assert ops[op] > 0, (key, op)
+		assert ops['STL'] == 0 and ops['LDL'] == 0, (key, 'spills to local memory')
+		assert any('PHASECHK' in i for i in ins) and not any('TRYWAIT' in i for i in ins), (key, 'mbarrier waits must be non-blocking probes')
+		assert any(i.startswith('MUFU.RSQ') for i in ins)
+		if bars is not None:
+			assert ops['BAR'] == bars, (key, ops['BAR'])
