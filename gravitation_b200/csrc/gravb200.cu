@@ -218,8 +218,8 @@ SymVariant make_sym64(const char* name) {
 #define VSYM64(T, R, TILE, ST, MB, U) make_sym64<T, R, TILE, ST, MB, U>("f64sym_t" #T "_r" #R "_j" #TILE "_s" #ST "_b" #MB "_u" #U)
 const std::vector<SymVariant>& variants_sym64() {
     static const std::vector<SymVariant> v = {
-        VSYM64(256, 6, 256, 3, 1, 2),   // 100 auto: one GPU, N >= 2^15 (IBLK 1536)
-        VSYM64(256, 8, 256, 3, 1, 1),   // 101 auto: power-of-two IBLK 2048 (shards of several GPUs)
+        VSYM64(256, 6, 256, 3, 1, 2),   // 100 (IBLK 1536)
+        VSYM64(256, 8, 256, 3, 1, 1),   // 101 auto: N >= 2^14 on one GPU and on shards of several GPUs (IBLK 2048)
         VSYM64(256, 4, 128, 3, 2, 2),   // 102 auto: medium N (IBLK 1024)
         VSYM64(256, 4, 256, 3, 2, 2),   // 103
         VSYM64(256, 4, 256, 3, 2, 1),   // 104
@@ -243,20 +243,28 @@ const std::vector<SymVariant>& variants_sym_of(int dtype) { return dtype == GRAV
 // trades a few per cent of imbalance for not falling back to the ordered sweep (-28 %).  The last shard must
 // keep at least one row.  Small universes keep the plain partition (ordered sweep or variant 101).
 constexpr int64_t kSymShardMinN = 32768;
+// symmetric variants a multi-shard run may use, fastest first, with their one-GPU rates at large N (T inter/s)
+struct SymChoice { int variant; double rate; };
+inline const SymChoice* sym_shard_choices(int dtype) {
+    static const SymChoice f32[2] = {{0, 3.65}, {1, 3.44}};   // IBLK 3072, 2048
+    static const SymChoice f64[2] = {{1, 1.52}, {0, 1.48}};   // IBLK 2048, 1536
+    return dtype == GRAVB200_F32 ? f32 : f64;
+}
 int64_t shard_chunk(int64_t n_total, int world, int dtype) {
     const int64_t plain = (n_total + world - 1) / world;
     if (world <= 1 || n_total < kSymShardMinN) return plain;
-    const double rate_sym[2] = {dtype == GRAVB200_F32 ? 3.65 : 1.46, dtype == GRAVB200_F32 ? 3.44 : 1.40};   // T inter/s
+    const SymChoice* ch = sym_shard_choices(dtype);
     const double rate_ordered = dtype == GRAVB200_F32 ? 2.62 : 1.01;
+    auto iblk_of = [&](int o) { const SymVariant& v = variants_sym_of(dtype)[ch[o].variant]; return (int64_t)v.threads * v.r; };
     int64_t best = plain;
-    double best_cost = (plain % ((int64_t)variants_sym_of(dtype)[1].threads * variants_sym_of(dtype)[1].r) == 0)
-                           ? (double)plain / rate_sym[1] : (double)plain / rate_ordered;
+    double best_cost = (double)plain / rate_ordered;
+    for (int o = 1; o >= 0; --o)   // the plain partition may already be whole blocks of a variant
+        if (plain % iblk_of(o) == 0) best_cost = (double)plain / ch[o].rate;
     for (int o = 0; o < 2; ++o) {
-        const SymVariant& v = variants_sym_of(dtype)[o];
-        const int64_t iblk = (int64_t)v.threads * v.r;
+        const int64_t iblk = iblk_of(o);
         const int64_t aligned = (plain + iblk - 1) / iblk * iblk;
         if ((int64_t)(world - 1) * aligned >= n_total) continue;   // would leave the last shard empty
-        const double cost = (double)aligned / rate_sym[o];
+        const double cost = (double)aligned / ch[o].rate;
         if (cost < 0.98 * best_cost) { best_cost = cost; best = aligned; }   // 2 % margin: the rates are estimates
     }
     return best;
@@ -434,16 +442,16 @@ int pick_variant(gravb200_ctx* c) {
         if (c->forced_variant >= kSymBase) sv = c->forced_variant - kSymBase;
         else if (c->forced_variant < 0 && c->n_total >= c->sym_min_n)
             sv = c->dtype == GRAVB200_F32 ? (c->n_total >= 65536 ? 0 : (c->n_total >= 16384 ? 1 : 6))
-                                          : (c->n_total >= 32768 ? 0 : 2);   // profiles/r01_sym*_variants_sweep*.txt
+                                          : (c->n_total >= 16384 ? 1 : 2);   // profiles/r01_sym*_variants_sweep*.txt
         if (sv >= 0) return setup_sym(c, sv);
     } else if (c->world > 1 && c->peer_mode && c->acc64) {
         int sv = -1;
         if (c->forced_variant >= kSymBase) sv = c->forced_variant - kSymBase;
         else if (c->forced_variant < 0 && c->n_total >= kSymShardMinN) {
-            // the one-GPU variant when the shards are whole blocks of it (shard_chunk), else the power-of-two one
-            // (N = 2^20 on 3 shards is whole blocks of both: the faster one wins)
-            const SymVariant& v0 = variants_sym_of(c->dtype)[0];
-            sv = c->chunk % ((long long)v0.threads * v0.r) == 0 ? 0 : 1;
+            // the fastest variant whose blocks the shards are whole multiples of (shard_chunk aligned them)
+            const SymChoice* ch = sym_shard_choices(c->dtype);
+            const SymVariant& v0 = variants_sym_of(c->dtype)[ch[0].variant];
+            sv = c->chunk % ((long long)v0.threads * v0.r) == 0 ? ch[0].variant : ch[1].variant;
         }
         if (sv >= 0) {
             const SymVariant& v = variants_sym_of(c->dtype)[sv];

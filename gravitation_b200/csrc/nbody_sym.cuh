@@ -426,8 +426,8 @@ constexpr size_t sym_smem_bytes() {
 // registers for the whole block row.  Per unordered pair: 3 DADD + 3 DFMA + 6 (MUFU.RSQ64H seed refined to
 // |d|^-3, see mass_over_r3) + 2 (both masses) + 6 DFMA = 20 FP64-pipe operations, i.e. 10 per ordered
 // interaction instead of the ordered sweep's 16.  14 32-bit SHFL move the j-body and its partials.
-// Dynamic shared memory: tile ring | mbarriers | j-partials [NWARPS][3][TILE] doubles (single buffered, two
-// CTA barriers per tile: a tile takes ~50 us).
+// Dynamic shared memory: tile ring | mbarriers (full, empty, jbar) | j-partials [2][NWARPS][3][TILE] doubles
+// (double buffered for the deferred combine).
 // Padding bodies sit at +-1e150: d2 stays finite, the refined |d|^-3 underflows to 0 (inf would give
 // inf * 0 = NaN in the refinement).
 // ------------------------------------------------------------------------------------------------
@@ -442,7 +442,8 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
     double4* tiles = reinterpret_cast<double4*>(smem_raw);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * TILE * sizeof(double4));
     uint64_t* empty_bar = full_bar + STAGES;
-    double* jpart = reinterpret_cast<double*>(empty_bar + STAGES);   // [NWARPS][3][TILE]
+    uint64_t* jbar = empty_bar + STAGES;                             // j-partials of a tile complete
+    double* jpart = reinterpret_cast<double*>(jbar + 1);             // [2][NWARPS][3][TILE]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long total = p.row_start[p.n_iblocks];
@@ -453,6 +454,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NWARPS); }
+        mbar_init(jbar, NWARPS);
         mbar_fence_init();
     }
     __syncthreads();
@@ -508,6 +510,32 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
     const int src_lane = (lane + 1) & 31;
     const double e2 = p.eps2_d;
 
+    // deferred j-side combine, exactly as in the fp32 kernel: arrive on `jbar` when this warp's partials of a
+    // tile are written, combine that tile inside the next one after the first ring round; no CTA barrier
+    bool jpend = false;
+    int jpend_n = 0, jpend_buf = 0, jbuf = 0;
+    long long jpend_j0 = 0;
+    uint32_t j_parity = 0;
+    auto combine_pending = [&]() {
+        mbar_wait_warp(jbar, j_parity);
+        j_parity ^= 1;
+        const double* jb = jpart + (size_t)jpend_buf * NWARPS * 3 * TILE;
+        for (int j = tid; j < jpend_n; j += THREADS) {
+            double ax = 0.0, ay = 0.0, az = 0.0;
+#pragma unroll
+            for (int wv = 0; wv < NWARPS; ++wv) {
+                ax += jb[(wv * 3 + 0) * TILE + j];
+                ay += jb[(wv * 3 + 1) * TILE + j];
+                az += jb[(wv * 3 + 2) * TILE + j];
+            }
+            double* dst = p.acc64 + (jpend_j0 + j) * 4;
+            atomicAdd(dst + 0, ax);
+            atomicAdd(dst + 1, ay);
+            atomicAdd(dst + 2, az);
+        }
+        jpend = false;
+    };
+
     for (int k = 0; k < ntiles; ++k) {
         if (new_row) {
             new_row = false;
@@ -562,8 +590,9 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (jpend) combine_pending();
         } else {
-            double* jp = jpart + (size_t)warp * 3 * TILE;
+            double* jp = jpart + ((size_t)jbuf * NWARPS + warp) * 3 * TILE;
 #pragma unroll 1
             for (int c = 0; c < CHUNKS; ++c) {
                 const int jl = c * 32 + lane;
@@ -597,25 +626,15 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
                     jy = __shfl_sync(0xffffffffu, jy, src_lane);
                     jz = __shfl_sync(0xffffffffu, jz, src_lane);
                 }
+                if (c == 0 && jpend) combine_pending();   // previous tile's j side (its buffer is the other one)
                 jp[0 * TILE + jl] = -jx;
                 jp[1 * TILE + jl] = -jy;
                 jp[2 * TILE + jl] = -jz;
             }
-            __syncthreads();
-            for (int j = tid; j < jn; j += THREADS) {
-                double ax = 0.0, ay = 0.0, az = 0.0;
-#pragma unroll
-                for (int wv = 0; wv < NWARPS; ++wv) {
-                    ax += jpart[(wv * 3 + 0) * TILE + j];
-                    ay += jpart[(wv * 3 + 1) * TILE + j];
-                    az += jpart[(wv * 3 + 2) * TILE + j];
-                }
-                double* dst = p.acc64 + (j0 + j) * 4;
-                atomicAdd(dst + 0, ax);
-                atomicAdd(dst + 1, ay);
-                atomicAdd(dst + 2, az);
-            }
-            __syncthreads();   // jpart is single buffered
+            __syncwarp();
+            if (lane == 0) mbar_arrive(jbar);
+            jpend = true; jpend_n = jn; jpend_j0 = j0; jpend_buf = jbuf;
+            jbuf ^= 1;
         }
 
         const int rowI = w.I;
@@ -634,6 +653,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
             new_row = true;
         }
     }
+    if (jpend) combine_pending();
     if (p.clk && blockIdx.x == 0 && tid == 0) {
         unsigned long long ns1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
@@ -644,7 +664,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
 
 template <int THREADS, int TILE, int STAGES>
 constexpr size_t sym64_smem_bytes() {
-    return (size_t)STAGES * TILE * sizeof(double4) + 2 * STAGES * sizeof(uint64_t) + (size_t)(THREADS / 32) * 3 * TILE * sizeof(double);
+    return (size_t)STAGES * TILE * sizeof(double4) + (2 * STAGES + 1) * sizeof(uint64_t) + (size_t)2 * (THREADS / 32) * 3 * TILE * sizeof(double);
 }
 
 // ------------------------------------------------------------------------------------------------

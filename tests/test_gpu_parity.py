@@ -527,23 +527,23 @@ def test_symmetric_sweep_on_two_gpus(oracle, gpu):
 	assert traj_err(r3, r_ref) <= 5e-6
 
 
-@pytest.mark.parametrize('dtype,n', (('float32', 1 << 18), ('float64', 1 << 17)))
+@pytest.mark.parametrize('dtype,n', (('float32', 1 << 18), ('float64', (1 << 17) + 1000)))
 def test_symmetric_sweep_on_block_aligned_shards(dtype, n, oracle, gpu):
 	"""large universes on several GPUs: the shards are whole body-blocks of the one-GPU symmetric variant
-	(gravb200_partition rounds ceil(N/P) up when the predicted step time is shorter), so every GPU runs variant 100; the last
+	(gravb200_partition rounds ceil(N/P) up when the predicted step time is shorter), so every GPU runs it; the last
 	shard is short.  Sampled rows against the oracle, then two more steps against a single GPU."""
 	if gpu.device_count() < 2:
 		pytest.skip('needs 2 GPUs')
 	from gravitation_b200.kernel import b200
 	parts = gpu.partition(n, 2, dtype)
-	iblk = 3072 if dtype == 'float32' else 1536
+	iblk, variant = (3072, gpu.SYM_BASE) if dtype == 'float32' else (2048, gpu.SYM_BASE + 1) # the fastest variant of each dtype
 	assert parts[0][1] % iblk == 0 and parts[0][1] > parts[1][1] > 0 and parts[0][1] + parts[1][1] == n
 	r, v, m, G, T = oracle.uniform_universe(n, 21, dtype)
 	u = b200.universe(T = T, G = G, scale_off = True, dtype = dtype, threads = 2)
 	u.add_objects(r, v, m, scale_off = True)
 	u.start()
 	assert [(sh.row0, sh.n_local) for sh in u._shards] == parts
-	assert all(sh.info()['variant'] == gpu.SYM_BASE and sh.info()['exchange_mode'] == gpu.XCHG_PEER for sh in u._shards)
+	assert all(sh.info()['variant'] == variant and sh.info()['exchange_mode'] == gpu.XCHG_PEER for sh in u._shards)
 	u.step_stage1()
 	a = np.array(u.accelerations())
 	rows = np.unique(np.concatenate([np.linspace(0, n - 1, 512).astype(np.int64), np.arange(parts[1][0] - 4, parts[1][0] + 4)]))

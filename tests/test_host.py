@@ -205,7 +205,8 @@ def test_row_partition_covers_all_rows(shim):
 	# the headline configuration: whole 3072-row blocks of the one-GPU symmetric variant on every full shard
 	parts = row_partition(1 << 20, 8, 'float32')
 	assert parts[0][1] == 43 * 3072 and all(r0 % 3072 == 0 for r0, _ in parts)
-	assert row_partition(1 << 18, 8, 'float64')[0][1] == 1 << 15 # 22 blocks of 1536 (+3 %) lose against 16 blocks of 2048
+	assert row_partition(1 << 18, 8, 'float64')[0][1] == 1 << 15 # already 16 blocks of 2048, the faster fp64 variant
+	assert row_partition((1 << 17) + 1000, 2, 'float64')[0][1] == 33 * 2048
 	assert row_partition(178225, 4, 'float32')[0][1] == 15 * 3072 # +3.4 % rows, but the symmetric sweep instead of the ordered one
 	assert row_partition(32768, 8, 'float32') == [(4096 * k, 4096) for k in range(8)] # 2 blocks of 3072 would empty the last shard
 
@@ -337,8 +338,8 @@ def test_row_partition_properties_hypothesis(shim):
 def test_sass_of_the_default_kernels(shim):
 	"""cuobjdump -sass of libgravb200.so (sm_100a): the automatic large-N variants stage j-tiles with TMA bulk
 	copies (UBLKCP) behind mbarriers probed without blocking (SYNCS.PHASECHK, no TRYWAIT), compute with packed
-	FFMA2 / DFMA and MUFU.RSQ, keep everything in registers (no local-memory spills), and the symmetric fp32
-	sweep has no CTA-wide barrier after its prologue (one BAR for the mbarrier initialisation)"""
+	FFMA2 / DFMA and MUFU.RSQ, keep everything in registers (no local-memory spills), and the symmetric
+	sweeps have no CTA-wide barrier after their prologue (one BAR for the mbarrier initialisation)"""
 	import collections, shutil, subprocess
 	tool = shutil.which('cuobjdump') or ('/usr/local/cuda/bin/cuobjdump' if os.path.isfile('/usr/local/cuda/bin/cuobjdump') else None)
 	if tool is None:
@@ -361,7 +362,7 @@ def test_sass_of_the_default_kernels(shim):
 		return collections.Counter(i.split()[0].split('.')[0] for i in ins), ins
 	for key, must, bars in (
 		('sym_sweep_kernelILi256ELi12ELi512ELi3ELi2E', ('UBLKCP', 'FFMA2', 'FADD2', 'FMUL2', 'MUFU', 'SHFL', 'REDG', 'VOTE'), 1), # fp32 symmetric, variant 100
-		('sym_sweep_kernel_f64ILi256ELi6ELi256ELi3ELi1ELi2E', ('UBLKCP', 'DFMA', 'MUFU', 'SHFL', 'REDG', 'VOTE'), 3), # fp64 symmetric, variant 100
+		('sym_sweep_kernel_f64ILi256ELi8ELi256ELi3ELi1ELi1E', ('UBLKCP', 'DFMA', 'MUFU', 'SHFL', 'REDG', 'VOTE'), 1), # fp64 symmetric, variant 101
 		('sweep_kernelIfLi256ELi8ELi512ELi3ELi1ELi1ELi4ELi1E', ('UBLKCP', 'FFMA2', 'FADD2', 'FMUL2', 'MUFU', 'VOTE'), None), # fp32 ordered, variant 0
 		('sweep_kernelIdLi256ELi2ELi256ELi3ELi2ELi0ELi4ELi0E', ('UBLKCP', 'DFMA', 'MUFU', 'VOTE'), None), # fp64 ordered, variant 0
 		):
