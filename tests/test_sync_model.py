@@ -118,3 +118,80 @@ def test_the_checker_finds_the_hazards_the_protocol_avoids():
 	assert 'holds tile' in explore('ssss', warps = 2, write_before_wait = True)
 	# a single buffer cannot hold tile k + 1 while tile k is still being combined
 	assert 'holds tile' in explore('sss', warps = 2, buffers = 1)
+
+
+# ---- the TMA tile ring (full / empty mbarriers, producer = first warp), same exhaustive treatment ---------
+
+def ring_programs(ntiles, warps, stages = 3, producer_skips_empty_wait = False):
+	"""per-thread event lists: warps 0..W-1 (warp 0 also produces, as in the kernels) and the TMA engine.
+	Mirrors the sweep loops: prefetch of STAGES-1 tiles, then per tile k: [producer: wait empty slot of tile
+	k+STAGES-1 if it was used before, issue that tile] ; wait full(k) ; read slot ; arrive empty."""
+	progs = [[] for _ in range(warps)]
+	issued = []
+	for k in range(min(ntiles, stages - 1)):
+		progs[0].append(('issue', k))
+		issued.append(k)
+	for k in range(ntiles):
+		kk = k + stages - 1
+		if kk < ntiles:
+			if kk >= stages and not producer_skips_empty_wait:
+				progs[0].append(('wait_empty', kk % stages, ((kk - stages) // stages) % 2))
+			progs[0].append(('issue', kk))
+			issued.append(kk)
+		for w in range(warps):
+			progs[w] += [('wait_full', k % stages, (k // stages) % 2), ('read', k % stages, k), ('arrive_empty', k % stages)]
+	progs.append([('land', k) for k in issued]) # the copy engine completes the bulk copies in issue order, whenever
+	return progs
+
+
+def explore_ring(ntiles, warps = 2, stages = 3, **kw):
+	progs = ring_programs(ntiles, warps, stages, **kw)
+	lens = [len(p) for p in progs]
+	seen, stack = set(), [tuple([0] * len(progs))]
+	while stack:
+		pcs = stack.pop()
+		if pcs in seen:
+			continue
+		seen.add(pcs)
+		if all(pc == n for pc, n in zip(pcs, lens)):
+			continue
+		# shared state from the executed prefixes
+		issued, content = set(), {}
+		full = [0] * stages # completed phases of full[s] (one per landed copy)
+		empty_arrivals = [0] * stages
+		for t, pc in enumerate(pcs):
+			for ev in progs[t][:pc]:
+				if ev[0] == 'issue':
+					issued.add(ev[1])
+				elif ev[0] == 'land':
+					content[ev[1] % stages] = ev[1]; full[ev[1] % stages] += 1
+				elif ev[0] == 'arrive_empty':
+					empty_arrivals[ev[1]] += 1
+		moved = False
+		for t, pc in enumerate(pcs):
+			if pc == lens[t]:
+				continue
+			ev = progs[t][pc]
+			if ev[0] == 'land' and ev[1] not in issued:
+				continue
+			if ev[0] == 'wait_full' and full[ev[1]] % 2 == ev[2]:
+				continue
+			if ev[0] == 'wait_empty' and (empty_arrivals[ev[1]] // warps) % 2 == ev[2]:
+				continue
+			if ev[0] == 'read' and content.get(ev[1]) != ev[2]:
+				return 'warp %d reads tile %d from slot %d, which holds tile %r (state %r)' % (t, ev[2], ev[1], content.get(ev[1]), pcs)
+			moved = True
+			stack.append(pcs[:t] + (pc + 1,) + pcs[t + 1:])
+		if not moved:
+			return 'deadlock at %r' % (pcs,)
+	return None
+
+
+@pytest.mark.parametrize('warps', (1, 2))
+def test_tile_ring_is_race_free_in_every_interleaving(warps):
+	for ntiles in (1, 2, 3, 4, 5, 7, 8):
+		assert explore_ring(ntiles, warps = warps) is None, ntiles
+
+
+def test_the_ring_checker_finds_a_producer_that_does_not_wait():
+	assert 'holds tile' in explore_ring(6, warps = 2, producer_skips_empty_wait = True)
