@@ -17,6 +17,19 @@ STATE_STOPPED = 2
 
 _STR_TEMPLATE = '{name} | {x:.4e}, {y:.4e}, {z:.4e} | {vx:.4e}, {vy:.4e}, {vz:.4e}'
 
+# Lifecycle rules of the front end as one table: (call, state it must NOT be made in) -> message of the
+# SyntaxError the reference raises in that situation (`_base_.py:110-113,124-127,139-142,167-170`).
+_LIFECYCLE_ERRORS = {
+	('add_object', STATE_STARTED): 'simulation was started',
+	('add_object', STATE_STOPPED): 'simulation was stopped',
+	('start', STATE_STARTED): 'simulation is running',
+	('start', STATE_STOPPED): 'simulation was stopped',
+	('step', STATE_PREINIT): 'simulation was not started',
+	('step', STATE_STOPPED): 'simulation was stopped',
+	('stop', STATE_PREINIT): 'simulation was not started',
+	('stop', STATE_STOPPED): 'simulation was stopped before',
+	}
+
 
 class _point_mass:
 	"""one body: `_name`, position `_r`, velocity `_v`, acceleration `_a` (3-sequences) and mass `_m`
@@ -69,6 +82,12 @@ class universe_base:
 		self._threads = threads
 		self._meta = kwargs
 
+	def _allow(self, call):
+		"""lifecycle guard: raises the reference's SyntaxError if `call` is not legal in the current state"""
+		message = _LIFECYCLE_ERRORS.get((call, self._state))
+		if message is not None:
+			raise SyntaxError(message)
+
 	def __iter__(self):
 		"""fixed front end: iterates the point masses"""
 		return (pm for pm in self._mass_list)
@@ -84,10 +103,7 @@ class universe_base:
 		"""adds one point mass (keywords name, r, v, m); only before `start`.
 		Unless `scale_off` is given, r and v are scaled by `scale_r` IN PLACE on the caller's lists and
 		m by `scale_m` (reference `_base_.py:107-118`).  Fixed front end."""
-		if self._state == STATE_STARTED:
-			raise SyntaxError('simulation was started')
-		if self._state == STATE_STOPPED:
-			raise SyntaxError('simulation was stopped')
+		self._allow('add_object')
 		if not kwargs.pop('scale_off', False):
 			for key in ('r', 'v'):
 				kwargs[key][:] = [component * self._scale_r for component in kwargs[key]]
@@ -96,10 +112,7 @@ class universe_base:
 
 	def start(self):
 		"""once, after adding objects and before stepping (reference `_base_.py:120-129`)"""
-		if self._state == STATE_STARTED:
-			raise SyntaxError('simulation is running')
-		if self._state == STATE_STOPPED:
-			raise SyntaxError('simulation was stopped')
+		self._allow('start')
 		self._state = STATE_STARTED
 		self.start_kernel()
 
@@ -109,10 +122,7 @@ class universe_base:
 	def step(self):
 		"""one time step = stage 1, stage 2, stage 3 in this order (reference `_base_.py:136-145`).
 		Fixed front end."""
-		if self._state == STATE_PREINIT:
-			raise SyntaxError('simulation was not started')
-		if self._state == STATE_STOPPED:
-			raise SyntaxError('simulation was stopped')
+		self._allow('step')
 		self.step_stage1()
 		self.step_stage2()
 		self.step_stage3()
@@ -132,10 +142,7 @@ class universe_base:
 
 	def stop(self):
 		"""once, after stepping (reference `_base_.py:163-172`)"""
-		if self._state == STATE_PREINIT:
-			raise SyntaxError('simulation was not started')
-		if self._state == STATE_STOPPED:
-			raise SyntaxError('simulation was stopped before')
+		self._allow('stop')
 		self._state = STATE_STOPPED
 		self.stop_kernel()
 

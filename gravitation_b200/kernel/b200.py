@@ -111,8 +111,7 @@ class universe(universe_base):
 	def add_objects(self, r, v, m, names = None, scale_off = False):
 		"""bulk `add_object`: r, v array-likes (N,3), m (N,).  Same unit scaling as `add_object`
 		(reference `_base_.py:114-117`) unless `scale_off`.  Must be the only way this universe is filled."""
-		if self._state != STATE_PREINIT:
-			raise SyntaxError('simulation was started' if self._state == 1 else 'simulation was stopped')
+		self._allow('add_object')
 		if len(self._mass_list) != 0:
 			raise SyntaxError('add_objects needs an empty universe')
 		r = np.array(r, dtype = np.float64)
@@ -129,8 +128,7 @@ class universe(universe_base):
 
 	def steps(self, k):
 		"""k full steps on the device without returning to Python in between"""
-		if self._state != 1:
-			raise SyntaxError('simulation was not started' if self._state == STATE_PREINIT else 'simulation was stopped')
+		self._allow('step')
 		if len(self._shards) == 1:
 			self._shards[0].steps(k)
 		else:
