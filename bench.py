@@ -198,6 +198,7 @@ def own_arm(args):
 	launches = shard.info()['launches'] - launches0
 	total_ms = dist.max_over_ranks(sum(step_ms)) if world > 1 else sum(step_ms)
 	info = shard.info()
+	rows_rank0 = shard.n_local
 	value = interactions * args.steps / (total_ms * 1e-3) / 1e9
 
 	shard.close()
@@ -320,7 +321,7 @@ def own_arm(args):
 			'grid': info['grid'], 'threads': info['threads'], 'bodies_per_thread': info['bodies_per_thread'], 'tile': info['tile'],
 			'l2': 'flushed between timed steps (256 MiB write); the 16 MiB position array is then re-read from L2 by design',
 			},
-		'per_gpu': {'g_inter_s': per_gpu_rate / 1e9, 'sweep_ms': float(np.mean(sweep_ms)), 'exchange_ms': float(np.mean(xchg_ms)),
+		'per_gpu': {'g_inter_s': per_gpu_rate / 1e9, 'rows_rank0': int(rows_rank0), 'rows_even_share': -(-n // world), 'sweep_ms': float(np.mean(sweep_ms)), 'exchange_ms': float(np.mean(xchg_ms)),
 			'sm_mhz_in_kernel': float(np.median(sm_mhz))},
 		'wall_ms_per_step': wall_ms / args.steps,
 		'clocks': clocks.summary(),
