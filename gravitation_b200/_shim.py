@@ -169,19 +169,18 @@ def sym_variant_names(dtype = 'float32'):
 	return [lib.gravb200_variant_name(d, SYM_BASE + k).decode() for k in range(lib.gravb200_sym_variant_count(d))]
 
 
-class PinnedArray:
-	"""owner of a page-locked host buffer exposed as a numpy array (`.array`); freed with the object"""
+class _PinnedBlock:
+	"""owns one cudaHostAlloc allocation and exposes it through the array interface, so every numpy view made
+	from it (`np.asarray(block)` and all views of that) keeps the block — and thereby the page-locked memory —
+	alive.  The memory is freed when the last view is gone, never earlier (no use-after-free through a row
+	view that outlives its universe)."""
 
-	def __init__(self, shape, dtype):
+	def __init__(self, nbytes):
 		self._lib = load()
-		dt = np.dtype(dtype)
-		nbytes = int(np.prod(shape)) * dt.itemsize
 		p = ctypes.c_void_p()
-		_check(self._lib.gravb200_host_alloc(nbytes, ctypes.byref(p)))
+		_check(self._lib.gravb200_host_alloc(max(int(nbytes), 1), ctypes.byref(p)))
 		self._p = p
-		buf = (ctypes.c_char * max(nbytes, 1)).from_address(p.value)
-		self.array = np.frombuffer(buf, dtype = dt, count = int(np.prod(shape))).reshape(shape)
-		self.array[...] = 0
+		self.__array_interface__ = {'shape': (max(int(nbytes), 1),), 'typestr': '|u1', 'data': (p.value, False), 'version': 3}
 
 	def __del__(self):
 		try:
@@ -190,6 +189,19 @@ class PinnedArray:
 				self._p = None
 		except Exception:
 			pass
+
+
+class PinnedArray:
+	"""a page-locked host buffer as a numpy array (`.array`).  The allocation belongs to the ARRAY (its base
+	chain ends in a `_PinnedBlock`), not to this wrapper: views handed out to callers stay valid after the
+	universe that created them is gone, like the reference's plain numpy arrays."""
+
+	def __init__(self, shape, dtype):
+		dt = np.dtype(dtype)
+		count = int(np.prod(shape))
+		block = _PinnedBlock(count * dt.itemsize)
+		self.array = np.asarray(block)[:count * dt.itemsize].view(dt).reshape(shape)
+		self.array[...] = 0
 
 
 def _ptr(a):
@@ -313,3 +325,30 @@ class Shard:
 			self.close()
 		except Exception:
 			pass
+
+
+def connect_peers(shard, want = None):
+	"""One process per GPU: switches `shard` to the fused peer-store exchange if EVERY rank of the
+	torch.distributed group can map every peer's buffers (CUDA IPC over NVLink); otherwise all ranks stay on
+	the NCCL all-gather.  The decision is collective — a mixed world would deadlock.  `want` False (or
+	GRAVB200_EXCHANGE=nccl) keeps NCCL.  torch.distributed is used for the rendezvous only (blob gather +
+	one MIN all-reduce), never on the data path.  Returns the mode in use (XCHG_PEER / XCHG_NCCL)."""
+	import torch
+	import torch.distributed as tdist
+	if want is None:
+		want = os.environ.get('GRAVB200_EXCHANGE', 'peer').lower() != 'nccl'
+	ok = 1
+	try:
+		blobs = [None] * shard.world
+		tdist.all_gather_object(blobs, shard.peer_export())
+		if want:
+			shard.peer_connect(blobs)
+	except GravB200Error:
+		ok = 0
+	t = torch.tensor([ok if want else 0], dtype = torch.int32)
+	if tdist.get_backend() == 'nccl':
+		t = t.cuda()
+	tdist.all_reduce(t, op = tdist.ReduceOp.MIN)
+	mode = XCHG_PEER if int(t.item()) == 1 else XCHG_NCCL
+	shard.set_exchange_mode(mode)
+	return mode

@@ -13,6 +13,7 @@ import argparse
 import json
 import subprocess
 import sys
+import tempfile
 
 from ..lib.load import inventory
 
@@ -58,17 +59,21 @@ def main(argv = None):
 			for threads in thread_list:
 				for bodies in size_range(*a.n_body_power_boundaries):
 					cmd = worker_command(name, bodies, threads, a.min_iterations, a.min_total_runtime, extra)
-					proc = subprocess.Popen(cmd, stdout = subprocess.PIPE, stderr = subprocess.PIPE, text = True)
-					for line in proc.stdout:
-						log.write(line)
-						try:
-							msg = json.loads(line)
-						except ValueError:
-							continue
-						if msg.get('log') == 'BEST_TIME':
-							best[(name, threads, bodies)] = msg['value']
-					err = proc.stderr.read()
-					proc.wait()
+					# stderr goes to a temp file, not a pipe: a chatty worker (NCCL_DEBUG, CUDA warnings) must never
+					# block on a full pipe while this loop is still reading its stdout
+					with tempfile.TemporaryFile('w+') as errfile:
+						proc = subprocess.Popen(cmd, stdout = subprocess.PIPE, stderr = errfile, text = True)
+						for line in proc.stdout:
+							log.write(line)
+							try:
+								msg = json.loads(line)
+							except ValueError:
+								continue
+							if msg.get('log') == 'BEST_TIME':
+								best[(name, threads, bodies)] = msg['value']
+						proc.wait()
+						errfile.seek(0)
+						err = errfile.read()
 					log.flush()
 					ns = best.get((name, threads, bodies))
 					print('%s@%d N=%d best=%s ns%s' % (name, threads, bodies, ns, ' [stderr: %s]' % err.strip()[-200:] if proc.returncode else ''))

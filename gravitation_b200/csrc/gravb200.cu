@@ -682,8 +682,14 @@ int exchange(gravb200_ctx* c) {
 // the symmetric sweep has left partial sums in the accumulator (one shard: the integrate kernel cleared
 // it; several: the clear belongs to the exchange that will not happen).
 int drop_pending(gravb200_ctx* c) {
-    if (c->pending && c->use_sym && c->world > 1 && c->acc64)
+    if (c->pending && c->use_sym && c->world > 1 && c->acc64) {
+        // the owners may still be reading this shard's partial sums (integrate kernel of the dropped step):
+        // same order as a regular exchange — step barrier first, then the clear.  Every rank drops the step
+        // (uploads and repeated stage1 calls are collective), so the barrier generations stay in lockstep.
+        int rc = peer_barrier(c);
+        if (rc) return rc;
         CU(cudaMemsetAsync(c->acc64, 0, (size_t)c->n_pad * 4 * sizeof(double), c->stream));
+    }
     c->pending = false;
     return 0;
 }
@@ -1014,6 +1020,9 @@ int gravb200_stage1(gravb200_ctx* c) {
     if (!c) return fail(GRAVB200_EINVAL, "ctx is NULL");
     if (!c->uploaded) return fail(GRAVB200_EINVAL, "no state uploaded");
     CU(cudaSetDevice(c->device));
+    // a second stage1 without a stage2 in between recomputes the same step: whatever the first one left in
+    // the multi-shard accumulator must not be added twice
+    if (c->pending) { int rc0 = drop_pending(c); if (rc0) return rc0; }
     CU(cudaEventRecord(c->ev[0], c->stream));
     int rc = launch_sweep(c, 1);
     if (rc) return rc;

@@ -66,28 +66,10 @@ def make_shard(n, dtype = 'float32'):
 
 
 def connect_peers(shard):
-	"""switches `shard` to the fused peer-store exchange if EVERY rank can map every peer's buffers
-	(CUDA IPC over NVLink); otherwise all ranks stay on the NCCL all-gather.  The decision is collective:
-	a mixed world would deadlock.  GRAVB200_EXCHANGE=nccl keeps NCCL.  Returns the mode in use."""
-	import torch
-	import torch.distributed as dist
+	"""collective switch to the fused peer-store exchange (all ranks or none); lives next to the binding so the
+	kernel module needs nothing but `_shim` inside the reference tree.  Returns the mode in use."""
 	from . import _shim
-	want = os.environ.get('GRAVB200_EXCHANGE', 'peer').lower() != 'nccl'
-	ok = 1
-	try:
-		blobs = [None] * shard.world
-		dist.all_gather_object(blobs, shard.peer_export())
-		if want:
-			shard.peer_connect(blobs)
-	except _shim.GravB200Error:
-		ok = 0
-	t = torch.tensor([ok if want else 0], dtype = torch.int32)
-	if dist.get_backend() == 'nccl':
-		t = t.cuda()
-	dist.all_reduce(t, op = dist.ReduceOp.MIN)
-	mode = _shim.XCHG_PEER if int(t.item()) == 1 else _shim.XCHG_NCCL
-	shard.set_exchange_mode(mode)
-	return mode
+	return _shim.connect_peers(shard)
 
 
 def gather_rows(local_rows, n, dtype = None):

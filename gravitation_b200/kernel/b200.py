@@ -33,14 +33,19 @@ __authors__ = [
 
 import os
 import threading
+import warnings
 
 import numpy as np
 
-from ._base_ import universe_base, _point_mass, STATE_PREINIT
+from ._base_ import universe_base, _point_mass, STATE_PREINIT, STATE_STARTED, STATE_STOPPED
 try: # inside this repository
 	from .. import _shim
 except ImportError: # dropped into the reference tree next to an underscore-prefixed `_b200_` package
 	from ._b200_ import _shim
+
+# Everything this module needs beyond numpy is `_base_` (only names the reference's own `_base_.py` has:
+# universe_base, _point_mass, STATE_*) and `_shim` — so the file works unchanged inside the reference tree
+# (tests/test_dropin.py installs it there).
 
 
 class _synced_list(list):
@@ -111,7 +116,10 @@ class universe(universe_base):
 	def add_objects(self, r, v, m, names = None, scale_off = False):
 		"""bulk `add_object`: r, v array-likes (N,3), m (N,).  Same unit scaling as `add_object`
 		(reference `_base_.py:114-117`) unless `scale_off`.  Must be the only way this universe is filled."""
-		self._allow('add_object')
+		if self._state == STATE_STARTED: # same guards and messages as `add_object` (reference `_base_.py:110-113`)
+			raise SyntaxError('simulation was started')
+		if self._state == STATE_STOPPED:
+			raise SyntaxError('simulation was stopped')
 		if len(self._mass_list) != 0:
 			raise SyntaxError('add_objects needs an empty universe')
 		r = np.array(r, dtype = np.float64)
@@ -128,14 +136,18 @@ class universe(universe_base):
 
 	def steps(self, k):
 		"""k full steps on the device without returning to Python in between"""
-		self._allow('step')
+		if self._state == STATE_PREINIT: # same guards and messages as `step` (reference `_base_.py:139-142`)
+			raise SyntaxError('simulation was not started')
+		if self._state == STATE_STOPPED:
+			raise SyntaxError('simulation was stopped')
 		if len(self._shards) == 1:
 			self._shards[0].steps(k)
 		else:
 			for _ in range(k):
 				self.step_stage1()
 				self._commit()
-		self._t += k * self._T
+		for _ in range(k): # k roundings, exactly like k calls of step_stage3 (`_base_.py:158-161`)
+			self._t += self._T
 		self._stale_rv = True
 		self._stale_a = True
 
@@ -198,8 +210,8 @@ class universe(universe_base):
 				rank = int(meta['rank']), world = int(meta['world']), nccl_id = meta.get('nccl_id'),
 				)
 			if int(meta['world']) > 1:
-				from ..dist import connect_peers
-				connect_peers(shard)
+				mode = _shim.connect_peers(shard, want = self._want_peer_exchange())
+				self._note_exchange(mode)
 			return [shard]
 		gpus = int(self._threads)
 		if gpus < 1:
@@ -226,18 +238,35 @@ class universe(universe_base):
 			raise errors[0]
 		# fused exchange: every shard maps every other shard's position buffers (direct peer access) and
 		# the sweep's epilogue stores r' there; all-or-nothing, NCCL all-gather otherwise
-		mode = _shim.XCHG_NCCL
-		if str(meta.get('exchange', os.environ.get('GRAVB200_EXCHANGE', 'peer'))).lower() != 'nccl':
+		mode, why = _shim.XCHG_NCCL, None
+		if self._want_peer_exchange():
 			try:
 				blobs = [sh.peer_export() for sh in shards]
 				for sh in shards:
 					sh.peer_connect(blobs)
 				mode = _shim.XCHG_PEER
-			except _shim.GravB200Error:
-				mode = _shim.XCHG_NCCL
+			except _shim.GravB200Error as e:
+				mode, why = _shim.XCHG_NCCL, str(e)
 		for sh in shards:
 			sh.set_exchange_mode(mode)
+		self._note_exchange(mode, why)
 		return shards
+
+	def _want_peer_exchange(self):
+		return str(self._meta.get('exchange', os.environ.get('GRAVB200_EXCHANGE', 'peer'))).lower() != 'nccl'
+
+	def _note_exchange(self, mode, why = None):
+		"""records the position exchange in use (`exchange_mode`: 'peer' | 'nccl') and, when the fused
+		peer-store exchange was wanted but is not available, says so loudly: the NCCL all-gather also rules out
+		the symmetric sweep on several shards, i.e. costs about a quarter of the throughput"""
+		self.exchange_mode = 'peer' if mode == _shim.XCHG_PEER else 'nccl'
+		self.exchange_fallback = None
+		if mode != _shim.XCHG_PEER and self._want_peer_exchange():
+			self.exchange_fallback = why or 'a rank could not map its peers (CUDA IPC / peer access)'
+			warnings.warn(
+				'b200 kernel: fused peer-store exchange unavailable (%s); falling back to the NCCL all-gather '
+				'with the ordered sweep (about 28 %% slower)' % self.exchange_fallback, RuntimeWarning, stacklevel = 2,
+				)
 
 	def step_stage1(self):
 		"""launches the sweep on every shard (asynchronous): accelerations + fused v', r' into back buffers"""

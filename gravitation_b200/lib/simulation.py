@@ -13,6 +13,7 @@ unseeded global `random`, `simulation.py:116`), and universes that offer `add_ob
 bulk, which is what makes N = 2^20 .. 2^24 constructible."""
 
 import math
+import os
 import random
 
 import numpy as np
@@ -148,27 +149,54 @@ def _snapshot_arrays(universe_obj):
 	return r, v, m, names
 
 
+def _h5py():
+	"""h5py if it is importable (it is an optional dependency here; the reference hard-imports it, `simulation.py:35`)"""
+	try:
+		import h5py
+		return h5py
+	except ImportError:
+		return None
+
+
+def _npz_path(fn):
+	return fn if fn.endswith('.npz') else fn + '.npz'
+
+
+def _plain(val):
+	"""HDF5 attribute / 0-d array -> plain Python value (str, int, float)"""
+	if isinstance(val, bytes):
+		return val.decode('utf-8')
+	if isinstance(val, np.ndarray) and val.ndim == 0:
+		val = val[()]
+	if isinstance(val, np.generic):
+		val = val.item()
+	if isinstance(val, bytes):
+		return val.decode('utf-8')
+	return val
+
+
 def store_simulation(universe_obj, fn, gn):
 	"""appends snapshot `gn` to file `fn`: datasets r, v (N x dim), m, name and the universe attributes.
-	HDF5 with the reference's layout if h5py is importable, else `<fn>.npz` with keys `<gn>/<dataset>`."""
+	HDF5 with the reference's layout (`simulation.py:216-258`: group `gn`, datasets `r`, `v`, `m` in the run
+	dtype, `name` as fixed-width bytes, attributes scale_m, scale_r, t, T, G, dtype, threads) if h5py is
+	importable and `fn` does not ask for `.npz`; otherwise `<fn>.npz` with keys `<gn>/<dataset>` and
+	`<gn>/attr/<attribute>`.  Returns the path written."""
 	r, v, m, names = _snapshot_arrays(universe_obj)
 	dtype = {'float32': '<f4', 'float64': '<f8'}[universe_obj._dtype]
 	attrs = {a: getattr(universe_obj, '_' + a) for a in _ATTRS}
-	try:
-		import h5py
-	except ImportError:
-		h5py = None
-	if h5py is not None:
+	name_array = np.array([s.encode('utf-8') for s in names]) # dtype 'S<longest name>', as `simulation.py:239-244`
+	h5py = _h5py()
+	if h5py is not None and not fn.endswith('.npz'):
 		with h5py.File(fn, 'a') as f:
 			dg = f.create_group(gn)
 			dg.create_dataset('r', data = r.astype(dtype))
 			dg.create_dataset('v', data = v.astype(dtype))
 			dg.create_dataset('m', data = m.astype(dtype))
-			dg.create_dataset('name', data = np.array([s.encode('utf-8') for s in names]))
+			dg.create_dataset('name', data = name_array)
 			for key, val in attrs.items():
 				dg.attrs[key] = val
 		return fn
-	path = fn if fn.endswith('.npz') else fn + '.npz'
+	path = _npz_path(fn)
 	store = {}
 	try:
 		with np.load(path, allow_pickle = False) as old:
@@ -178,23 +206,38 @@ def store_simulation(universe_obj, fn, gn):
 	store[gn + '/r'] = r.astype(dtype)
 	store[gn + '/v'] = v.astype(dtype)
 	store[gn + '/m'] = m.astype(dtype)
-	store[gn + '/name'] = np.array([s.encode('utf-8') for s in names])
+	store[gn + '/name'] = name_array
 	for key, val in attrs.items():
 		store[gn + '/attr/' + key] = np.array(val)
 	np.savez(path, **store)
 	return path
 
 
-def load_simulation(universe_class, fn, gn, threads = None):
-	"""rebuilds a (not yet started) universe from snapshot `gn` (`simulation.py:186-214`): values are
-	stored in internal units, hence `scale_off`"""
-	path = fn if fn.endswith('.npz') else fn + '.npz'
+def _read_snapshot(fn, gn):
+	"""(param dict, r, v, m, names) of snapshot `gn`: from the HDF5 file `fn` when there is one and h5py can
+	open it (`simulation.py:186-196`), else from the `.npz` twin `store_simulation` writes without h5py"""
+	h5py = _h5py()
+	if h5py is not None and not fn.endswith('.npz') and os.path.isfile(fn) and h5py.is_hdf5(fn):
+		with h5py.File(fn, 'r') as f:
+			dg = f[gn]
+			param = {str(key): _plain(dg.attrs[key]) for key in dg.attrs.keys()}
+			r, v, m, names = (np.array(dg[key]) for key in ('r', 'v', 'm', 'name'))
+		return param, r, v, m, names
+	path = _npz_path(fn)
+	if not os.path.isfile(path):
+		if os.path.isfile(fn):
+			raise OSError('%s is an HDF5 snapshot file, but h5py is not importable here' % fn)
+		raise FileNotFoundError('no snapshot file %s (or %s)' % (fn, path))
 	with np.load(path, allow_pickle = False) as f:
-		param = {}
-		for key in _ATTRS:
-			val = f[gn + '/attr/' + key]
-			param[key] = val.item() if val.dtype.kind != 'U' else str(val)
+		param = {key: _plain(f[gn + '/attr/' + key]) for key in _ATTRS}
 		r, v, m, names = f[gn + '/r'], f[gn + '/v'], f[gn + '/m'], f[gn + '/name']
+	return param, r, v, m, names
+
+
+def load_simulation(universe_class, fn, gn, threads = None):
+	"""rebuilds a (not yet started) universe from snapshot `gn` of file `fn` (`simulation.py:186-214`): values
+	are stored in internal units, hence `scale_off`"""
+	param, r, v, m, names = _read_snapshot(fn, gn)
 	if isinstance(threads, int):
 		param['threads'] = threads
 	universe_obj = universe_class(scale_off = True, **param)

@@ -136,12 +136,93 @@ def test_solarsystem_and_unknown_scenario(golden):
 
 def test_snapshot_roundtrip(tmp_path):
 	u = simulation.create_simulation('galaxy', _recorder, {'stars_len': 32, 'seed': 1})
-	fn = str(tmp_path / 'data.h5')
+	fn = str(tmp_path / 'data.npz') # the .npz twin, whatever is installed
 	path = simulation.store_simulation(u, fn, 'kernel=x;len=32;step=0')
+	assert path == fn
 	u2 = simulation.load_simulation(_recorder, path, 'kernel=x;len=32;step=0')
 	r, v, m = _state(u); r2, v2, m2 = _state(u2)
 	assert np.array_equal(r.astype('f4'), r2.astype('f4')) and np.array_equal(m.astype('f4'), m2.astype('f4'))
 	assert u2._G == u._G and u2._T == u._T and u2._dtype == 'float32' and list(u2)[0]._name == 'back hole'
+	with pytest.raises(FileNotFoundError):
+		simulation.load_simulation(_recorder, str(tmp_path / 'nothing.h5'), 'x')
+
+
+def _hdf5_roundtrip(tmp_path, h5py):
+	"""store -> inspect the file with `h5py` -> load; the layout is the reference's (`simulation.py:216-258`)"""
+	u = simulation.create_simulation('galaxy', _recorder, {'stars_len': 32, 'seed': 1})
+	fn = str(tmp_path / 'data.h5')
+	groups = ['kernel=x;len=32;step=0', 'kernel=x;len=32;step=5']
+	assert simulation.store_simulation(u, fn, groups[0]) == fn # what the writer returns is what the reader takes
+	u._t = 5 * u._T
+	assert simulation.store_simulation(u, fn, groups[1]) == fn # append mode: a second group in the same file
+	with h5py.File(fn, 'r') as f:
+		assert sorted(f.keys()) == sorted(groups)
+		dg = f[groups[1]]
+		assert dg['r'].shape == (32, 3) and dg['v'].shape == (32, 3) and dg['m'].shape == (32,) and dg['name'].shape == (32,)
+		assert np.dtype(dg['r'].dtype) == np.dtype('<f4') and np.dtype(dg['m'].dtype) == np.dtype('<f4')
+		assert np.dtype(dg['name'].dtype) == np.dtype('S9') and bytes(dg['name'][0]) == b'back hole'
+		assert sorted(dg.attrs.keys()) == sorted(['scale_m', 'scale_r', 't', 'T', 'G', 'dtype', 'threads'])
+	u2 = simulation.load_simulation(_recorder, fn, groups[1], threads = 3)
+	r, v, m = _state(u); r2, v2, m2 = _state(u2)
+	assert np.array_equal(r.astype('f4'), r2.astype('f4')) and np.array_equal(v.astype('f4'), v2.astype('f4'))
+	assert np.array_equal(m.astype('f4'), m2.astype('f4'))
+	assert u2._G == u._G and u2._T == u._T and u2._t == u._t and u2._dtype == 'float32' and u2._threads == 3
+	assert type(u2._dtype) is str and type(u2._T) is float
+	assert [pm._name for pm in u2][:2] == ['back hole', 'star']
+	assert simulation.load_simulation(_recorder, fn, groups[0])._t == 0.0
+
+
+def test_snapshot_hdf5_branch_with_a_stand_in_h5py(tmp_path, monkeypatch):
+	"""h5py is absent from this image: the HDF5 branches of store/load run against tests/fake_h5py.py"""
+	import sys
+	sys.path.insert(0, os.path.join(ROOT, 'tests'))
+	import fake_h5py
+	monkeypatch.setitem(sys.modules, 'h5py', fake_h5py)
+	_hdf5_roundtrip(tmp_path, fake_h5py)
+	# an HDF5 file without h5py: a clear error instead of "data.h5.npz not found"
+	monkeypatch.setitem(sys.modules, 'h5py', None)
+	with pytest.raises(OSError, match = 'h5py is not importable'):
+		simulation.load_simulation(_recorder, str(tmp_path / 'data.h5'), 'kernel=x;len=32;step=0')
+
+
+def test_snapshot_hdf5_layout_with_real_h5py(tmp_path):
+	h5py = pytest.importorskip('h5py')
+	_hdf5_roundtrip(tmp_path, h5py)
+
+
+def test_pinned_views_keep_their_memory_alive(monkeypatch):
+	"""a row view that outlives its universe must not point at freed page-locked memory.
+	The allocation belongs to the numpy base chain; it is released when the LAST view goes."""
+	import ctypes
+	import gc
+	from gravitation_b200 import _shim
+	libc = ctypes.CDLL(None)
+	libc.malloc.restype = ctypes.c_void_p
+	libc.malloc.argtypes = [ctypes.c_size_t]
+	libc.free.argtypes = [ctypes.c_void_p]
+	freed = []
+
+	class _fake_lib:
+		@staticmethod
+		def gravb200_host_alloc(nbytes, out):
+			out._obj.value = libc.malloc(nbytes)
+			return 0
+		@staticmethod
+		def gravb200_host_free(p):
+			freed.append(p.value)
+			libc.free(p)
+			return 0
+	monkeypatch.setattr(_shim, 'load', lambda: _fake_lib)
+	holder = _shim.PinnedArray((7, 3), 'float64')
+	assert holder.array.shape == (7, 3) and holder.array.dtype == np.float64 and not holder.array.any()
+	holder.array[3, :] = (1.0, 2.0, 3.0)
+	row = holder.array[3, :]
+	del holder
+	gc.collect()
+	assert freed == [] and list(row) == [1.0, 2.0, 3.0] # still valid, still owned
+	del row
+	gc.collect()
+	assert len(freed) == 1
 
 
 def test_timers():
@@ -266,6 +347,75 @@ def test_benchmark_size_range_matches_reference_rule():
 	assert size_range(2, 4) == [4, 6, 8, 12, 16] and size_range(3, 3) == [8]
 	cmd = worker_command('b200', 4096, 2, 10, 0)
 	assert cmd[1:3] == ['-m', 'gravitation_b200.cli.worker'] and '{"stars_len": 4096}' in cmd and cmd[-1] == '2'
+
+
+# ---- npnn: the independent float64 numpy kernel of the inventory -------------------
+
+def _npnn(n, dtype, seed = 42, scenario = 'galaxy'):
+	from gravitation_b200.kernel import npnn
+	param = {'dtype': dtype, 'seed': seed}
+	if scenario == 'galaxy':
+		param['stars_len'] = n
+	return simulation.create_simulation(scenario, npnn.universe, param)
+
+
+@pytest.mark.parametrize('case,n,scenario', (('solarsystem', 2, 'solarsystem'), ('galaxy256', 256, 'galaxy'), ('galaxy4096', 4096, 'galaxy')))
+def test_npnn_is_pinned_to_the_reference_goldens(case, n, scenario, golden, oracle):
+	"""accelerations and 10-step trajectories of the N x N numpy kernel at float64 against what the REFERENCE's
+	np2 at float64 (and py1) produced (tests/golden/make_golden.py); different summation order, same physics"""
+	g = golden[case]
+	u = _npnn(n, 'float64', scenario = scenario)
+	assert 'npnn' in load.inventory and np.array_equal(u.mass_r_array, g['r0'])
+	u.step_stage1()
+	assert oracle.max_rel_err(u.mass_a_array, g['acc_np2_f64']) < 1e-12
+	if 'acc_py1' in g:
+		assert oracle.max_rel_err(u.mass_a_array, g['acc_py1']) < 1e-12
+	first = [pm for pm in u][n - 1]
+	assert np.array_equal(np.asarray(first._a), u.mass_a_array[n - 1, :]) # point masses are row views
+	u.step_stage2(); u.step_stage3()
+	for _ in range(9):
+		u.step()
+	scale = np.abs(g['r10_np2_f64']).max()
+	assert np.abs(u.mass_r_array - g['r10_np2_f64']).max() / scale < 1e-12
+	assert oracle.max_rel_err(u.mass_v_array, g['v10_np2_f64']) < 1e-10
+	assert u._t == 10 * u._T
+	u.stop()
+
+
+def test_npnn_float32_state_is_within_the_reference_fp32_envelope(golden, oracle):
+	g = golden['galaxy256']
+	u = _npnn(256, 'float32')
+	assert u.mass_r_array.dtype == np.float32 and np.array_equal(u.mass_r_array, g['r0_f32'])
+	u.step_stage1()
+	assert oracle.max_rel_err(u.mass_a_array, g['acc_np2_f64']) < 1e-6 # input rounding only: the arithmetic is float64
+	for _ in range(10):
+		u.step()
+	assert oracle.max_rel_err(u.mass_r_array[1:], g['r10_np2_f64'][1:]) < 5e-6
+
+
+def test_benchmark_cli_sweeps_dtype_through_worker_and_analyze(tmp_path):
+	"""SURVEY 8f rank 4 end to end on the CPU kernel: `benchmark` spawns one worker per (threads, N) with the
+	dtype riding in --scenario_param, the log parses, and `analyze --summary` has the dtype / threads / N axes"""
+	import json
+	from gravitation_b200.cli import analyze, benchmark
+	log = str(tmp_path / 'bench.log')
+	for dtype in ('float32', 'float64'):
+		rc = benchmark.main(['-k', 'npnn', '-b', '5', '6', '-i', '2', '-t', '0', '-p', '1', '-p', '2', '-l', log,
+			'--scenario_param', json.dumps({'dtype': dtype, 'seed': 3})])
+		assert rc == 0
+	analyze.main(['-l', log, '-o', str(tmp_path / 'bench.json'), '--summary'])
+	rows = json.loads((tmp_path / 'bench.json.summary.json').read_text())
+	# npnn is not parallel: `-p 1 -p 2` collapses to threads = 1 (benchmark.py:188-192 of the reference)
+	assert [(r['kernel'], r['dtype'], r['threads'], r['bodies']) for r in rows] == [
+		('npnn', dt, 1, n) for dt in ('float32', 'float64') for n in (32, 48, 64)]
+	assert all(r['steps'] >= 2 and r['g_interactions_per_s'] > 0 for r in rows)
+
+
+def test_accuracy_cli_compares_two_kernel_runs(capsys):
+	from gravitation_b200.cli import accuracy
+	out = accuracy.main(['-k', 'npnn', '--dtype', 'float32', '--ref_kernel', 'npnn', '--ref_dtype', 'float64', '-n', '128', '-s', '3'])
+	assert out['test'] == {'kernel': 'npnn', 'dtype': 'float32'} and out['reference'] == {'kernel': 'npnn', 'dtype': 'float64'}
+	assert 0 < out['acceleration_max_rel'] < 1e-6 and 0 < out['position_max_rel'] < 5e-6 and out['bodies'] == 128
 
 
 # ---- bench.py contract: exactly one JSON line on stdout, whatever libraries print ------------------
