@@ -39,6 +39,8 @@ _SIGNATURES = [
 		ctypes.c_double, ctypes.c_double, ctypes.c_double,
 		]),
 	('gravb200_upload_positions', ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
+	('gravb200_upload_rows', ctypes.c_int, [_c_ctx, ctypes.c_void_p, ctypes.c_void_p]),
+	('gravb200_download_rows', ctypes.c_int, [_c_ctx, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
 	('gravb200_stage1', ctypes.c_int, [_c_ctx]),
 	('gravb200_stage2', ctypes.c_int, [_c_ctx]),
 	('gravb200_exchange', ctypes.c_int, [_c_ctx]),
@@ -245,6 +247,25 @@ class Shard:
 		r = self._arr(r, (self.n_total, 3))
 		_check(self._lib.gravb200_upload_positions(self._ctx, _ptr(r)))
 
+	def upload_rows(self, r_own, v_own = None):
+		"""this shard's rows only ([n_local, 3] each); collective over the shards of a universe"""
+		r_own = self._arr(r_own, (self.n_local, 3))
+		if v_own is not None:
+			v_own = self._arr(v_own, (self.n_local, 3))
+		_check(self._lib.gravb200_upload_rows(self._ctx, _ptr(r_own), _ptr(v_own)))
+
+	def download_rows(self, r = True, v = True, a = False, out_r = None, out_v = None, out_a = None):
+		"""this shard's rows only: (r, v, a), each [n_local, 3] or None"""
+		outs = []
+		for want, arr in ((r, out_r), (v, out_v), (a, out_a)):
+			if want and arr is None:
+				arr = np.empty((self.n_local, 3), dtype = self._np)
+			if want and not (arr.flags.c_contiguous and arr.dtype == self._np and arr.shape == (self.n_local, 3)):
+				raise ValueError('download targets must be C-contiguous (n_local, 3) arrays of dtype %s' % self.dtype)
+			outs.append(arr if want else None)
+		_check(self._lib.gravb200_download_rows(self._ctx, _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2])))
+		return tuple(outs)
+
 	def upload_raw(self, r_ptr, v_ptr, m_ptr, G, T, eps = 0.0):
 		"""host pointers (ints) of C-contiguous buffers in the context dtype, e.g. pinned memory"""
 		_check(self._lib.gravb200_upload(self._ctx, r_ptr, v_ptr, m_ptr, G, T, eps))
@@ -299,9 +320,12 @@ class Shard:
 		return (out_r if r else None, out_v if v else None, out_a if a else None)
 
 	def timings(self):
-		ms = (ctypes.c_float * 5)()
-		_check(self._lib.gravb200_timings(self._ctx, ms, 5))
-		return dict(sweep_ms = ms[0], exchange_ms = ms[1], steps_ms = ms[2], sm_mhz = ms[3], cta0_ms = ms[4])
+		ms = (ctypes.c_float * 10)()
+		_check(self._lib.gravb200_timings(self._ctx, ms, 10))
+		out = dict(sweep_ms = ms[0], exchange_ms = ms[1], steps_ms = ms[2], sm_mhz = ms[3], cta0_ms = ms[4])
+		if ms[5] >= 0: # several shards, symmetric sweep: where the step's time went
+			out['phases_ms'] = dict(sweep_kernel = ms[5], wait_sweeps = ms[6], integrate = ms[7], step_barrier = ms[8], clear = ms[9])
+		return out
 
 	def info(self):
 		v = (ctypes.c_int64 * 12)()

@@ -321,6 +321,8 @@ struct gravb200_ctx {
     unsigned long long* clk = nullptr;   // {SM cycles, ns} of CTA 0 of the last sweep
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t tev[6] = {};   // several shards: sweep start | sweep end | barrier | integrate | step barrier | clear (gravb200_timings ms[5..9])
+    bool tev_ok = false;
     bool ev_sweep = false, ev_xchg = false, ev_steps = false;
     ncclComm_t comm = nullptr;
     int sm_count = 0;
@@ -543,7 +545,10 @@ int launch_sweep(gravb200_ctx* c, int integrate) {
         sp.eps2_f = (float)(c->eps * c->eps);
         sp.clk = c->clk;
         void* sargs[] = {&sp};
+        const bool trace = c->world > 1 && c->tev[0];
+        if (trace) CU(cudaEventRecord(c->tev[0], c->stream));
         CU(cudaLaunchKernel(sv.fn, dim3(c->grid), dim3(sv.threads), sargs, sv.smem, c->stream));
+        if (trace) CU(cudaEventRecord(c->tev[1], c->stream));
         IntegrateParams ip;
         memset(&ip, 0, sizeof(ip));
         ip.sp.pos_front = c->pos[c->front];
@@ -564,6 +569,7 @@ int launch_sweep(gravb200_ctx* c, int integrate) {
             // every shard's sweep must be complete before the owners read the partial sums
             int rc = peer_barrier(c);
             if (rc) return rc;
+            if (trace) CU(cudaEventRecord(c->tev[2], c->stream));
             for (int q = 0; q < c->world; ++q) {
                 ip.acc_src[ip.n_src++] = c->peer_acc[q];
                 if (q != c->rank) ip.sp.peer_back[ip.sp.n_peers++] = c->peer_pos[c->front ^ 1][q];
@@ -573,6 +579,7 @@ int launch_sweep(gravb200_ctx* c, int integrate) {
         if (c->dtype == GRAVB200_F32) sym_integrate_kernel<float><<<gb, 256, 0, c->stream>>>(ip);
         else sym_integrate_kernel<double><<<gb, 256, 0, c->stream>>>(ip);
         CU(cudaGetLastError());
+        if (trace) CU(cudaEventRecord(c->tev[3], c->stream));
         c->launches += 2;
         return 0;
     }
@@ -667,8 +674,11 @@ int exchange(gravb200_ctx* c) {
     if (c->peer_mode) {   // the data already travelled in the sweep's epilogue
         int rc = peer_barrier(c);
         if (rc) return rc;
+        const bool trace = c->use_sym && c->tev[0];
+        if (trace) CU(cudaEventRecord(c->tev[4], c->stream));
         // symmetric sweep: all owners have read this shard's partial sums; clear them for the next step
         if (c->use_sym) CU(cudaMemsetAsync(c->acc64, 0, (size_t)c->n_pad * 4 * sizeof(double), c->stream));
+        if (trace) { CU(cudaEventRecord(c->tev[5], c->stream)); c->tev_ok = true; }
         return 0;
     }
     char* back = (char*)c->pos[c->front ^ 1];
@@ -740,6 +750,72 @@ int download_impl(gravb200_ctx* c, void* r, void* v, void* a) {
         unpack_kernel<REAL, V4><<<(unsigned)((nl + tb - 1) / tb), tb, 0, c->stream>>>((const V4*)c->acc, (REAL*)c->stage3, nl);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(a, c->stage3, (size_t)nl * 3 * sizeof(REAL), cudaMemcpyDeviceToHost, c->stream));
+        c->launches++;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// Own rows only (several shards, each fed by its own host): positions and velocities of rows
+// [row0, row0 + n_local) come from the host, the masses stay, and the device exchange hands the new positions
+// to every other shard — NVLink copies into the peers' front buffers + the flag barrier (peer mode) or an
+// in-place all-gather (NCCL mode).  Collective: every shard of the universe must call it.
+template <typename REAL, typename V4>
+int upload_rows_impl(gravb200_ctx* c, const void* r_own, const void* v_own) {
+    const long long nl = c->n_local;
+    const int tb = 256;
+    const unsigned gl = (unsigned)((nl + tb - 1) / tb);
+    V4* front = (V4*)c->pos[c->front];
+    if (nl > 0) {
+        CU(cudaMemcpyAsync(c->stage3, r_own, (size_t)nl * 3 * sizeof(REAL), cudaMemcpyHostToDevice, c->stream));
+        pack_rm_kernel<REAL, V4><<<gl, tb, 0, c->stream>>>((const REAL*)c->stage3, nullptr, front + c->row0, nl);
+        CU(cudaGetLastError());
+        c->launches++;
+        if (v_own) {
+            REAL* vstage = (REAL*)c->stage3;   // reused after the pack above (stream ordered)
+            CU(cudaMemcpyAsync(vstage, v_own, (size_t)nl * 3 * sizeof(REAL), cudaMemcpyHostToDevice, c->stream));
+            pack_v_kernel<REAL, V4><<<gl, tb, 0, c->stream>>>((const REAL*)vstage, (V4*)c->vel[c->front], nl);
+            CU(cudaGetLastError());
+            c->launches++;
+        }
+    }
+    // the host buffers are the caller's again; everything below is device to device and only ENQUEUED (a host
+    // thread that drives several shards calls them one after the other and must not block on a peer here)
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->world > 1) {
+        if (c->peer_mode) {
+            if (nl > 0)
+                for (int q = 0; q < c->world; ++q)
+                    if (q != c->rank)
+                        CU(cudaMemcpyAsync((V4*)c->peer_pos[c->front][q] + c->row0, front + c->row0, (size_t)nl * sizeof(V4),
+                                           cudaMemcpyDefault, c->stream));
+            int rc = peer_barrier(c);   // all rows have landed everywhere before any shard sweeps
+            if (rc) return rc;
+        } else {
+            char* base = (char*)c->pos[c->front];
+            NC(g_nccl.AllGather(base + (size_t)c->rank * c->chunk * sizeof(V4), base, (size_t)c->chunk * 4,
+                                c->dtype == GRAVB200_F32 ? ncclFloat32 : ncclFloat64, c->comm, c->stream));
+        }
+    }
+    return 0;
+}
+
+template <typename REAL, typename V4>
+int download_rows_impl(gravb200_ctx* c, void* r_own, void* v_own, void* a_own) {
+    const int tb = 256;
+    const long long nl = c->n_local;
+    if (nl <= 0) return 0;
+    const unsigned gl = (unsigned)((nl + tb - 1) / tb);
+    // three disjoint thirds of the staging buffer when it is large enough (several shards), else one after the other
+    const bool apart = (size_t)c->n_total >= (size_t)3 * (size_t)nl;
+    const V4* src[3] = {(const V4*)c->pos[c->front] + c->row0, (const V4*)c->vel[c->front], (const V4*)c->acc};
+    void* dst[3] = {r_own, v_own, a_own};
+    for (int k = 0; k < 3; ++k) {
+        if (!dst[k]) continue;
+        REAL* stage = (REAL*)c->stage3 + (apart ? (size_t)k * nl * 3 : 0);
+        unpack_kernel<REAL, V4><<<gl, tb, 0, c->stream>>>(src[k], stage, nl);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(dst[k], stage, (size_t)nl * 3 * sizeof(REAL), cudaMemcpyDeviceToHost, c->stream));
         c->launches++;
     }
     CU(cudaStreamSynchronize(c->stream));
@@ -906,6 +982,7 @@ int gravb200_ctx_create(int64_t n_total, int dtype, int device, int rank, int wo
     } while (0)
     CUX(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto& ev : c->ev) CUX(cudaEventCreate(&ev));
+    if (world > 1) for (auto& ev : c->tev) CUX(cudaEventCreate(&ev));
     const size_t v4 = 4 * c->esz;
     for (int b = 0; b < 2; ++b) {
         CUX(cudaMalloc(&c->pos[b], (size_t)c->n_pad * v4));
@@ -974,6 +1051,8 @@ int gravb200_ctx_destroy(gravb200_ctx* c) {
     if (c->xerr) cudaFree(c->xerr);
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->tev)
+        if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -1014,6 +1093,24 @@ int gravb200_upload_positions(gravb200_ctx* c, const void* r) {
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+int gravb200_upload_rows(gravb200_ctx* c, const void* r_own, const void* v_own) {
+    if (!c) return fail(GRAVB200_EINVAL, "ctx is NULL");
+    if (!c->uploaded) return fail(GRAVB200_EINVAL, "gravb200_upload must come first (masses, G, T)");
+    if (!r_own && c->n_local > 0) return fail(GRAVB200_EINVAL, "r_own is NULL");
+    CU(cudaSetDevice(c->device));
+    int rc = drop_pending(c);
+    if (rc) return rc;
+    return c->dtype == GRAVB200_F32 ? upload_rows_impl<float, float4>(c, r_own, v_own) : upload_rows_impl<double, double4>(c, r_own, v_own);
+}
+
+int gravb200_download_rows(gravb200_ctx* c, void* r_own, void* v_own, void* a_own) {
+    if (!c) return fail(GRAVB200_EINVAL, "ctx is NULL");
+    if (!c->uploaded) return fail(GRAVB200_EINVAL, "no state uploaded");
+    CU(cudaSetDevice(c->device));
+    return c->dtype == GRAVB200_F32 ? download_rows_impl<float, float4>(c, r_own, v_own, a_own)
+                                    : download_rows_impl<double, double4>(c, r_own, v_own, a_own);
 }
 
 int gravb200_stage1(gravb200_ctx* c) {
@@ -1148,12 +1245,14 @@ int gravb200_timings(gravb200_ctx* c, float* ms, int n) {
         CU(cudaMemcpy(h, c->clk, sizeof(h), cudaMemcpyDeviceToHost));
         ms[3] = h[1] ? (float)((double)h[0] / (double)h[1] * 1e3) : -1.f;   // cycles/ns -> MHz
         if (n > 4) ms[4] = (float)((double)h[1] * 1e-6);   // lifetime of CTA 0 of the last sweep, ms
+        if (n > 9 && c->tev_ok && c->use_sym && c->world > 1 && cudaEventQuery(c->tev[5]) == cudaSuccess)
+            for (int i = 0; i < 5; ++i) CU(cudaEventElapsedTime(&ms[5 + i], c->tev[i], c->tev[i + 1]));
 #ifdef SYM_DEBUG
-        if (n > 6) {   // [2036..2046] divergence counters of SYM_DIVCHK, [2047] cycles spent in jbar waits
+        if (n > 16) {   // [2036..2046] divergence counters of SYM_DIVCHK, [2047] cycles spent in jbar waits
             unsigned long long d[12];
             CU(cudaMemcpy(d, c->clk + 2036, sizeof(d), cudaMemcpyDeviceToHost));
-            ms[5] = (float)d[10]; ms[6] = (float)((double)d[11] * 1e-6);
-            for (int i = 0; i < 10 && 7 + i < n; ++i) ms[7 + i] = (float)d[i];
+            ms[10] = (float)d[10]; ms[11] = (float)((double)d[11] * 1e-6);
+            for (int i = 0; i < 10 && 12 + i < n; ++i) ms[12 + i] = (float)d[i];
             CU(cudaMemset(c->clk + 2036, 0, sizeof(d)));
         }
 #endif

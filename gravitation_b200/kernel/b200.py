@@ -157,9 +157,16 @@ class universe(universe_base):
 		return self.mass_a_array
 
 	def push_host_state(self):
-		"""re-upload positions/velocities after the caller edited the host mirrors"""
-		for sh in self._shards:
-			sh.upload(self.mass_r_array, self.mass_v_array, self.mass_m_array, self._G, self._T, self._eps)
+		"""re-upload positions/velocities after the caller edited the host mirrors (masses, G, T stay).
+		One process per GPU with `host_rows='own'`: every rank sends only its own rows and the device exchange
+		(NVLink) completes the position array on all shards — collective, like `start()`."""
+		if self._own_rows_only:
+			sh = self._shards[0]
+			rows = slice(sh.row0, sh.row0 + sh.n_local)
+			sh.upload_rows(self.mass_r_array[rows, :], self.mass_v_array[rows, :])
+		else:
+			for sh in self._shards:
+				sh.upload(self.mass_r_array, self.mass_v_array, self.mass_m_array, self._G, self._T, self._eps)
 		self._stale_rv = self._stale_a = False
 
 	# ---------------------------------------------------------------------------------------------
@@ -176,6 +183,11 @@ class universe(universe_base):
 			raise ValueError('empty universe')
 		self._eps = float(self._meta.get('eps', 0.0))
 		self._eager = bool(self._meta.get('eager_host', False))
+		# one process per GPU: 'all' (default) mirrors all positions on every rank, 'own' only this rank's rows
+		# (velocities and accelerations exist for own rows only in either case)
+		self._own_rows_only = 'world' in self._meta and int(self._meta['world']) > 1 and self._meta.get('host_rows', 'all') == 'own'
+		if self._meta.get('host_rows', 'all') not in ('all', 'own'):
+			raise ValueError("host_rows must be 'all' or 'own'")
 		n = self.MASS_LEN
 		# host mirrors, laid out like the reference's numpy kernels (np2.py:63-66)
 		# (page-locked, so the on-demand downloads and `push_host_state` run at full PCIe rate)
@@ -311,6 +323,15 @@ class universe(universe_base):
 		if self._state == STATE_PREINIT or not getattr(self, '_shards', None):
 			return
 		if not (self._stale_rv or self._stale_a):
+			return
+		if self._own_rows_only:
+			sh = self._shards[0]
+			rows = slice(sh.row0, sh.row0 + sh.n_local)
+			sh.download_rows(
+				r = self._stale_rv, v = self._stale_rv, a = self._stale_a,
+				out_r = self.mass_r_array[rows, :], out_v = self.mass_v_array[rows, :], out_a = self.mass_a_array[rows, :],
+				)
+			self._stale_rv = self._stale_a = False
 			return
 		for k, sh in enumerate(self._shards):
 			rows = slice(sh.row0, sh.row0 + sh.n_local)

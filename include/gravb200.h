@@ -64,6 +64,17 @@ int gravb200_upload(gravb200_ctx* ctx, const void* r, const void* v, const void*
 /* Positions only (a caller that moved bodies on the host between steps, e.g. pc2's host-side stage 2). */
 int gravb200_upload_positions(gravb200_ctx* ctx, const void* r);
 
+/* Several shards, each fed by its own host buffer (replaces the same per-step copies, pc2.py:149-151, without
+ * every shard re-sending ALL bodies): r_own, v_own = [n_local][3] rows [row0, row0 + n_local) of this shard
+ * (v_own may be NULL: positions only); masses, G, T stay as gravb200_upload left them.  The device exchange
+ * (NVLink peer copies + flag barrier, or the NCCL all-gather) completes the position array on every shard.
+ * COLLECTIVE: every shard of the universe must call it, like gravb200_upload.  Returns when the host buffers
+ * may be reused; the device-side exchange is enqueued (NCCL mode with several shards in one host thread:
+ * bracket the calls with gravb200_group_begin/end, as for gravb200_exchange). */
+int gravb200_upload_rows(gravb200_ctx* ctx, const void* r_own, const void* v_own);
+/* The mirror image for reads (pc2.py:160-162): r_own, v_own, a_own = [n_local][3] of this shard's rows only. */
+int gravb200_download_rows(gravb200_ctx* ctx, void* r_own, void* v_own, void* a_own);
+
 /* Replaces: step_stage1() (pc2.py:147-162 kernel launch).  Asynchronous.  Computes accelerations of
  * this shard's rows AND, in the same kernel's epilogue, v' and r' into back buffers; front state is
  * untouched, so accelerations can be read between stage1 and stage2 as with every reference kernel. */
@@ -106,7 +117,10 @@ int gravb200_partition(int64_t n_total, int dtype, int world, int rank, int64_t*
 
 /* Device-side timings (cudaEvent): ms[0] = last stage1 sweep kernel, ms[1] = last exchange,
  * ms[2] = total of the last gravb200_steps() call, ms[3] = SM clock (MHz) that CTA 0 of the last sweep
- * observed over its lifetime (clock64 / globaltimer), ms[4] = that lifetime in ms; n = capacity of ms. */
+ * observed over its lifetime (clock64 / globaltimer), ms[4] = that lifetime in ms; several shards with the
+ * symmetric sweep, last complete step: ms[5] = sweep kernel, ms[6] = wait for all shards' sweeps (flag barrier),
+ * ms[7] = integrate kernel (peer loads of the partial sums + peer stores of r'), ms[8] = step barrier,
+ * ms[9] = accumulator clear; entries that do not apply are -1; n = capacity of ms. */
 int gravb200_timings(gravb200_ctx* ctx, float* ms, int n);
 
 /* Introspection used by bench.py / tests: launch geometry and counters.

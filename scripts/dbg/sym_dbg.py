@@ -20,8 +20,8 @@ for k, name in enumerate(names):
     out = []
     for _ in range(3):
         sh.stage1(); sh.stage2()
-        ms = (ctypes.c_float * 7)()
-        sh._lib.gravb200_timings(sh._ctx, ms, 7)
-        out.append((round(ms[0], 3), ms[5], round(ms[6], 3)))
+        ms = (ctypes.c_float * 22)()
+        sh._lib.gravb200_timings(sh._ctx, ms, 22)
+        out.append((round(ms[0], 3), ms[10], round(ms[11], 3)))
     print(json.dumps(dict(lib=os.path.basename(sys.argv[1]), n=n, variant=name, runs=out)), flush=True)
 sh.close()

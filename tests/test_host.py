@@ -134,6 +134,53 @@ def test_solarsystem_and_unknown_scenario(golden):
 		simulation.create_simulation('nope', _recorder)
 
 
+class _bulk_recorder(universe_base):
+	def add_objects(self, r, v, m, names = None, scale_off = False):
+		self.bulk = (np.array(r) * self._scale_r, np.array(v) * self._scale_r, np.array(m) * self._scale_m, names)
+	def step_stage1(self):
+		pass
+
+
+def test_vectorised_galaxy_builder_has_the_reference_construction():
+	"""above 2^16 bodies the galaxy comes from the numpy restatement of `simulation.py:114-184`
+	(own seeded stream, not bit-identical).  Checked: body 0 is the central mass, 80 / 20 split, radius ranges,
+	z-jitter envelope, circular-orbit speed from the universe's G, velocity at a right angle to the radius"""
+	n = 65536 + 8
+	u = simulation.create_simulation('galaxy', _bulk_recorder, {'stars_len': n, 'seed': 7})
+	R, V, M, names = u.bulk
+	assert R.shape == (n, 3) and len(names) == n and names[0] == 'back hole' and names[5] == 'star'
+	assert M[0] == 4e40 * 1e-30 and np.all(M[1:] == 2e30 * 1e-30) and not R[0].any() and not V[0].any()
+	rad = 1e20 * 1e-10
+	stars, n_disc = n - 1, (n - 1) * 4 // 5
+	rho = np.linalg.norm(R[1:], axis = 1)
+	disc_rho = np.linalg.norm(R[1:1 + n_disc, :2], axis = 1)
+	assert disc_rho.min() >= 0.1 * rad and disc_rho.max() < 4.6 * rad and disc_rho.max() > 4.5 * rad
+	assert np.all(np.abs(R[1:1 + n_disc, 2]) <= 0.25 * rad * (4.6 * rad - disc_rho) / (4.6 * rad) * (1 + 1e-12))
+	assert rho[n_disc:].min() >= 0.1 * rad * (1 - 1e-12) and rho[n_disc:].max() < 0.85 * rad
+	assert np.abs(R[1 + n_disc:, 2]).max() > 0.5 * rad # the bulge is three-dimensional
+	# orbit speed as the reference computes it: the universe's scaled G with UNSCALED lengths (`simulation.py:148`)
+	speed = np.linalg.norm(V[1:], axis = 1)
+	assert np.allclose(speed, np.sqrt(u._G * 4e40 / (rho / 1e-10)) * 1e-10, rtol = 1e-12)
+	assert np.abs((R[1:, :2] * V[1:, :2]).sum(1)).max() < 1e-9 * rad * speed.max() and not V[1:, 2].any()
+	again = simulation.create_simulation('galaxy', _bulk_recorder, {'stars_len': n, 'seed': 7}).bulk
+	other = simulation.create_simulation('galaxy', _bulk_recorder, {'stars_len': n, 'seed': 8}).bulk
+	assert np.array_equal(again[0], R) and not np.array_equal(other[0], R)
+	# below the switch the reference's own stream is kept (bit-identical universes); either builder can be forced
+	small = simulation.create_simulation('galaxy', _bulk_recorder, {'stars_len': 4200, 'seed': 42})
+	ref = simulation.create_simulation('galaxy', _recorder, {'stars_len': 4200, 'seed': 42})
+	assert np.array_equal(small.bulk[0], _state(ref)[0])
+	forced = simulation.create_simulation('galaxy', _bulk_recorder, {'stars_len': 4200, 'seed': 42, 'builder': 'vector'})
+	assert not np.array_equal(forced.bulk[0], small.bulk[0])
+	with pytest.raises(ValueError, match = 'Unknown galaxy builder'):
+		simulation.create_simulation('galaxy', _bulk_recorder, {'stars_len': 64, 'builder': 'nope'})
+	# tilt and turn act on positions and velocities alike (rotation about x, then about z)
+	R0, V0, _ = simulation.galaxy_arrays(1000, 1.0, [0.0] * 3, [0.0] * 3, 0.0, 0.0, 10.0, 1.0, 1.0, seed = 1)
+	R1, V1, _ = simulation.galaxy_arrays(1000, 1.0, [1.0, 2.0, 3.0], [4.0, 5.0, 6.0], 0.3, 0.2, 10.0, 1.0, 1.0, seed = 1)
+	cb, sb, ca, sa = np.cos(0.2), np.sin(0.2), np.cos(0.3), np.sin(0.3)
+	rot = np.array([[ca, -sa, 0], [sa, ca, 0], [0, 0, 1.0]]) @ np.array([[1.0, 0, 0], [0, cb, -sb], [0, sb, cb]])
+	assert np.allclose(R1[1:], R0[1:] @ rot.T + [1.0, 2.0, 3.0]) and np.allclose(V1[1:], V0[1:] @ rot.T + [4.0, 5.0, 6.0])
+
+
 def test_snapshot_roundtrip(tmp_path):
 	u = simulation.create_simulation('galaxy', _recorder, {'stars_len': 32, 'seed': 1})
 	fn = str(tmp_path / 'data.npz') # the .npz twin, whatever is installed
@@ -427,7 +474,7 @@ def test_bench_reference_arm_prints_one_json_line():
 	root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 	if not os.path.isfile(os.path.join(root, 'oracle', '_ref', 'lib4.so')) and not os.path.isfile(os.path.join(root, 'oracle', 'liboracle.so')):
 		pytest.skip('oracle not built')
-	out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '3'],
+	out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '3', '--bodies', '14'],
 		capture_output = True, text = True, timeout = 600)
 	assert out.returncode == 0, out.stderr[-2000:]
 	lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
@@ -436,6 +483,9 @@ def test_bench_reference_arm_prints_one_json_line():
 	assert line['impl'] == 'reference' and line['unit'] == 'G interactions/s' and line['higher_is_better'] is True
 	assert line['value'] > 0 and line['e2e']['value'] == line['value'] and line['e2e']['h2d_bytes_per_step'] == 0
 	assert line['cpu_baseline']['kind'] in ('reference', 'port') and line['cpu_baseline']['cores'] >= 1
+	# the line names the size it actually ran, not the size it stands in for
+	assert line['config']['n_bodies'] == 1 << 14 and line['config']['sampled_from_n_bodies'] == 1 << 20
+	assert line['config']['same_config'] is False and 'N=2^14' in line['config']['workload'] and '2^14' in line['cpu_baseline']['sample']
 
 
 # ---- the symmetric sweep's work decomposition, replayed on the host (csrc/nbody_sym.cuh) ------------
