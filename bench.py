@@ -329,7 +329,7 @@ def e2e_leg(env, n, dtype, state, steps, warmup):
 def pipe_model(info, dtype, shim):
 	"""executed work per ORDERED interaction (the metric's unit): ordered sweep 12 FP32-pipe lane-ops = 19 FLOP,
 	symmetric sweep (every unordered pair once, both bodies updated) 8 lane-ops = 13 FLOP; fp64: 16 / 10 ops"""
-	symmetric = info.get('variant', 0) >= shim.SYM_BASE
+	symmetric = shim.SYM_BASE <= info.get('variant', 0) < shim.SMALL_BASE
 	lane_ops = (8.0 if symmetric else 12.0) if dtype == 'float32' else (10.0 if symmetric else 16.0)
 	flop_exec = (13.0 if symmetric else 19.0) if dtype == 'float32' else (16.0 if symmetric else 25.0)
 	return symmetric, lane_ops, flop_exec

@@ -59,6 +59,8 @@ _SIGNATURES = [
 	('gravb200_set_variant', ctypes.c_int, [_c_ctx, ctypes.c_int]),
 	('gravb200_variant_count', ctypes.c_int, [ctypes.c_int]),
 	('gravb200_sym_variant_count', ctypes.c_int, [ctypes.c_int]),
+	('gravb200_small_variant_count', ctypes.c_int, []),
+	('gravb200_small_geometry', ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
 	('gravb200_variant_name', ctypes.c_char_p, [ctypes.c_int, ctypes.c_int]),
 	('gravb200_device_ptr', ctypes.c_void_p, [_c_ctx, ctypes.c_int]),
 	('gravb200_host_alloc', ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
@@ -143,7 +145,8 @@ def peak_probe(device = 0):
 	return dict(fp32_tflops = out[0], fp32x2_tflops = out[1], fp64_tflops = out[2], mufu_gops = out[3], sm_mhz = out[4])
 
 
-SYM_BASE = 100 # ids of the symmetric fp32 sweeps start here
+SYM_BASE = 100 # ids of the symmetric sweeps start here
+SMALL_BASE = 200 # ids of the persistent multi-step kernel for small universes start here
 
 
 def variant_names(dtype = 'float32'):
@@ -169,6 +172,22 @@ def sym_variant_names(dtype = 'float32'):
 	lib = load()
 	d = _DTYPES[dtype]
 	return [lib.gravb200_variant_name(d, SYM_BASE + k).decode() for k in range(lib.gravb200_sym_variant_count(d))]
+
+
+def small_variant_names():
+	"""persistent small-N kernels (ids SMALL_BASE + k; the same list for both dtypes)"""
+	lib = load()
+	return [lib.gravb200_variant_name(_DTYPES['float32'], SMALL_BASE + k).decode() for k in range(lib.gravb200_small_variant_count())]
+
+
+def small_geometry(n, dtype = 'float32', sm_count = 148, variant = SMALL_BASE):
+	"""geometry of the persistent small-N kernel (needs no device): dict(grid, rows_per_cta, row_groups, slice,
+	slices, smem_bytes, fits); raises when `n` needs more rows per CTA than the variant has lanes for"""
+	out = (ctypes.c_int64 * 6)()
+	rc = load().gravb200_small_geometry(int(n), _DTYPES[dtype], int(sm_count), int(variant), out, 6)
+	if rc < 0:
+		_check(rc)
+	return dict(grid = out[0], rows_per_cta = out[1], row_groups = out[2], slice = out[3], slices = out[4], smem_bytes = out[5], fits = rc == 0)
 
 
 class _PinnedBlock:
@@ -323,8 +342,8 @@ class Shard:
 		ms = (ctypes.c_float * 10)()
 		_check(self._lib.gravb200_timings(self._ctx, ms, 10))
 		out = dict(sweep_ms = ms[0], exchange_ms = ms[1], steps_ms = ms[2], sm_mhz = ms[3], cta0_ms = ms[4])
-		if ms[5] >= 0: # several shards, symmetric sweep: where the step's time went
-			out['phases_ms'] = dict(sweep_kernel = ms[5], wait_sweeps = ms[6], integrate = ms[7], step_barrier = ms[8], clear = ms[9])
+		if ms[5] >= 0: # several shards, symmetric sweep: where the step's time went (the integrate kernel starts by waiting for every shard's sweep, the tail by waiting for every shard's integrate)
+			out['phases_ms'] = dict(sweep_kernel = ms[5], integrate_incl_wait_for_sweeps = ms[6], tail_wait = ms[7])
 		return out
 
 	def info(self):

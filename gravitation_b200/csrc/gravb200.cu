@@ -12,6 +12,7 @@
 #include "../../include/gravb200.h"
 #include "nbody_kernels.cuh"
 #include "nbody_sym.cuh"
+#include "nbody_small.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -20,6 +21,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -234,40 +236,45 @@ const std::vector<SymVariant>& variants_sym64() {
 }
 const std::vector<SymVariant>& variants_sym_of(int dtype) { return dtype == GRAVB200_F32 ? variants_sym() : variants_sym64(); }
 
-// Rows per shard (contiguous slices, the last one short).  Several shards can run the
-// symmetric sweep only on whole body-blocks of a variant, so the shard size is chosen by predicted step time:
-// ceil(n / world) rounded up to blocks of symmetric variant 100 (IBLK 3072 fp32 / 1536 fp64) or 101 (IBLK
-// 2048) at their measured rates, against the plain ceil(n / world) with the ordered sweep
-// (profiles/r01_sym_variants_sweep2.txt, r01_sym64_variants_sweep.txt, one B200, large N).  N = 2^20 fp32 on
-// 8 GPUs: 43 blocks = 132 096 rows instead of 131 072 (+0.8 %) for the 6 % faster variant; an arbitrary N
-// trades a few per cent of imbalance for not falling back to the ordered sweep (-28 %).  The last shard must
-// keep at least one row.  Small universes keep the plain partition (ordered sweep or variant 101).
-constexpr int64_t kSymShardMinN = 32768;
-// symmetric variants a multi-shard run may use, fastest first, with their one-GPU rates at large N (T inter/s)
-struct SymChoice { int variant; double rate; };
-inline const SymChoice* sym_shard_choices(int dtype) {
-    static const SymChoice f32[2] = {{0, 3.65}, {1, 3.44}};   // IBLK 3072, 2048
-    static const SymChoice f64[2] = {{1, 1.52}, {0, 1.48}};   // IBLK 2048, 1536
-    return dtype == GRAVB200_F32 ? f32 : f64;
+// Persistent multi-step kernel for universes that fit one SM's shared memory (nbody_small.cuh), ids >= kSmallBase.
+struct SmallVariant {
+    const char* name;
+    int threads, unroll, r;
+    const void* fn[2];   // [GRAVB200_F32, GRAVB200_F64]
+};
+template <int THREADS, int UNROLL, int R>
+SmallVariant make_small(const char* name) {
+    SmallVariant v;
+    v.name = name;
+    v.threads = THREADS; v.unroll = UNROLL; v.r = R;
+    v.fn[0] = (const void*)&small_steps_kernel<float, THREADS, UNROLL, R>;
+    v.fn[1] = (const void*)&small_steps_kernel<double, THREADS, UNROLL, R>;
+    return v;
 }
-int64_t shard_chunk(int64_t n_total, int world, int dtype) {
-    const int64_t plain = (n_total + world - 1) / world;
-    if (world <= 1 || n_total < kSymShardMinN) return plain;
-    const SymChoice* ch = sym_shard_choices(dtype);
-    const double rate_ordered = dtype == GRAVB200_F32 ? 2.62 : 1.01;
-    auto iblk_of = [&](int o) { const SymVariant& v = variants_sym_of(dtype)[ch[o].variant]; return (int64_t)v.threads * v.r; };
-    int64_t best = plain;
-    double best_cost = (double)plain / rate_ordered;
-    for (int o = 1; o >= 0; --o)   // the plain partition may already be whole blocks of a variant
-        if (plain % iblk_of(o) == 0) best_cost = (double)plain / ch[o].rate;
-    for (int o = 0; o < 2; ++o) {
-        const int64_t iblk = iblk_of(o);
-        const int64_t aligned = (plain + iblk - 1) / iblk * iblk;
-        if ((int64_t)(world - 1) * aligned >= n_total) continue;   // would leave the last shard empty
-        const double cost = (double)aligned / ch[o].rate;
-        if (cost < 0.98 * best_cost) { best_cost = cost; best = aligned; }   // 2 % margin: the rates are estimates
-    }
-    return best;
+#define VSMALL(T, U, R) make_small<T, U, R>("small_t" #T "_u" #U "_r" #R)
+constexpr int kSmallBase = 200;
+const std::vector<SmallVariant>& variants_small() {
+    static const std::vector<SmallVariant> v = {
+        VSMALL(256, 4, 4),   // 200 auto: four rows per lane, the quarter-warps read four adjacent j-bodies
+        VSMALL(256, 4, 2),   // 201 two rows per lane (bound by shared-memory reads)
+        VSMALL(512, 4, 4),   // 202
+        VSMALL(256, 2, 4),   // 203
+        VSMALL(256, 2, 8),   // 204
+        VSMALL(256, 1, 8),   // 205
+        VSMALL(512, 2, 4),   // 206
+    };
+    return v;
+}
+constexpr size_t kSmallMaxSmem = 227 * 1024;
+
+// Rows per shard (contiguous slices of ceil(n / world) rows, the last one short).  The rows
+// a shard OWNS (integrates, keeps velocities of) no longer shape the symmetric sweep: its flat (row, tile) list
+// of the whole universe is cut into one equal range per shard (stream-K across GPUs, setup_sym), so no block
+// alignment is needed and every N keeps the fastest variant.  (Round 1 rounded the shards up to whole blocks:
+// +0.8 % rows on seven of eight GPUs at N = 2^20.)
+constexpr int64_t kSymShardMinN = 32768;   // automatic choice on several shards: symmetric sweep from this N on
+int64_t shard_chunk(int64_t n_total, int world, int /*dtype*/) {
+    return (n_total + world - 1) / world;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -321,7 +328,7 @@ struct gravb200_ctx {
     unsigned long long* clk = nullptr;   // {SM cycles, ns} of CTA 0 of the last sweep
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t tev[6] = {};   // several shards: sweep start | sweep end | barrier | integrate | step barrier | clear (gravb200_timings ms[5..9])
+    cudaEvent_t tev[6] = {};   // several shards, symmetric: sweep start | sweep end | integrate end | tail wait end (gravb200_timings ms[5..7])
     bool tev_ok = false;
     bool ev_sweep = false, ev_xchg = false, ev_steps = false;
     ncclComm_t comm = nullptr;
@@ -338,6 +345,12 @@ struct gravb200_ctx {
     double* peer_acc[kMaxPeers + 1] = {};
     bool peer_is_ipc[kMaxPeers + 1] = {};
     unsigned long long epoch = 0;                 // barrier generation, advanced in lockstep on all ranks
+    // symmetric sweep on several shards: hand-over flags live behind the barrier flags in the same allocation
+    // ([kFlagsSweep + q]: shard q's sweep of step e is done, [kFlagsIntegrate + q]: its integrate), one arrival
+    // counter per kernel, and the step generation (lockstep on all ranks)
+    unsigned int* done_ctr = nullptr;             // [2]
+    unsigned long long sym_epoch = 0;
+    bool sym_tail_pending = false;                // the last enqueued step has not been followed by its tail wait
     // symmetric sweep (fp32): global fp64 accumulator and the flat-item offsets of the local block rows
     double* acc64 = nullptr;
     long long* row_start = nullptr;
@@ -345,7 +358,13 @@ struct gravb200_ctx {
     bool use_sym = false;
     long long sym_min_n = 8192;    // automatic choice: symmetric sweep from this N on
     int sym_variant = 0, sym_blocks = 0, sym_gblocks = 0;
-    long long sym_total = 0;
+    long long sym_total = 0, sym_lo = 0, sym_hi = 0;   // flat items of the universe, this shard's share
+    // persistent small-N kernel (nbody_small.cuh): geometry, grid barrier counter and its host mirror
+    bool use_small = false;
+    int small_variant = 0, small_ng = 1, small_rpc = 0, small_slice = 0;
+    size_t small_smem = 0;
+    unsigned long long* gbar = nullptr;
+    unsigned long long gbar_count = 0;
     // gravb200_steps on one GPU, launch-bound sizes: kGraphSteps steps captured once per front-buffer parity
     cudaGraphExec_t step_graph[2] = {nullptr, nullptr};
     int64_t step_graph_kernels = 0;   // kernel nodes in one of them
@@ -388,10 +407,11 @@ int setup_sym(gravb200_ctx* c, int sv) {
     const SymVariant& v = variants_sym_of(c->dtype)[sv];
     const int iblk = v.threads * v.r;
     const int Bt = (int)((c->n_total + iblk - 1) / iblk);
-    const int nib = (int)((c->n_local + iblk - 1) / iblk);
-    const int g0 = (int)(c->row0 / iblk);
+    // one shard: its block rows are all block rows.  Several shards: every shard walks the GLOBAL list and takes
+    // its equal share of it (sym_items), independent of the rows it owns.
+    const int nib = Bt;
     std::vector<long long> rs((size_t)nib + 1, 0);
-    for (int i = 0; i < nib; ++i) rs[i + 1] = rs[i] + sym_row_tiles(c->n_total, iblk, v.tile, Bt, g0 + i);
+    for (int i = 0; i < nib; ++i) rs[i + 1] = rs[i] + sym_row_tiles(c->n_total, iblk, v.tile, Bt, i);
     if ((size_t)nib + 1 > c->row_start_n) {
         if (c->row_start) CU(cudaFree(c->row_start));
         c->row_start = nullptr;
@@ -412,15 +432,91 @@ int setup_sym(gravb200_ctx* c, int sv) {
     c->sym_blocks = nib;
     c->sym_gblocks = Bt;
     c->sym_total = rs[nib];
+    c->sym_lo = sk_lo(rs[nib], c->rank, c->world);
+    c->sym_hi = sk_lo(rs[nib], c->rank + 1, c->world);
     c->occ = occ;
-    c->grid = (int)std::max<long long>(1, std::min<long long>((long long)occ * c->sm_count, rs[nib]));
+    c->grid = (int)std::max<long long>(1, std::min<long long>((long long)occ * c->sm_count, c->sym_hi - c->sym_lo));
     c->use_sym = true;
+    return 0;
+}
+
+struct SmallGeometry { int grid, rpc, ng, slice, nsl; size_t smem; };
+// 0: fits; 1: more than 32 * NWARPS rows per CTA needed; 2: does not fit in shared memory
+int small_geometry(long long n, int dtype, int sm_count, const SmallVariant& v, SmallGeometry* g) {
+    const int nw = v.threads / 32;
+    int ng = 1;
+    while ((n + 32LL * ng - 1) / (32LL * ng) > sm_count && ng < nw) ng *= 2;
+    if ((n + 32LL * ng - 1) / (32LL * ng) > sm_count) return 1;
+    g->ng = ng;
+    g->grid = (int)((n + 32LL * ng - 1) / (32LL * ng));
+    g->rpc = (int)((n + g->grid - 1) / g->grid);
+    g->rpc += g->rpc & 1;
+    g->nsl = nw / ng;
+    const int q = v.r * v.unroll;
+    g->slice = (int)(((n + g->nsl - 1) / g->nsl + q - 1) / q * q);
+    g->smem = dtype == GRAVB200_F32 ? small_smem_bytes<float>(g->nsl * g->slice, g->nsl, ng) : small_smem_bytes<double>(g->nsl * g->slice, g->nsl, ng);
+    return g->smem > kSmallMaxSmem ? 2 : 0;
+}
+
+int setup_small(gravb200_ctx* c, int sv, bool forced) {
+    const SmallVariant& v = variants_small()[sv];
+    SmallGeometry g;
+    const int fit = small_geometry(c->n_total, c->dtype, c->sm_count, v, &g);
+    if (fit == 1) return forced ? fail(GRAVB200_EINVAL, "variant %s: %lld bodies need more than %d rows per CTA", v.name, (long long)c->n_total, v.threads) : 1;
+    if (fit == 2) return forced ? fail(GRAVB200_EINVAL, "variant %s: %lld bodies do not fit in shared memory (%zu bytes)", v.name, (long long)c->n_total, g.smem) : 1;
+    if (!forced && g.ng > (c->dtype == GRAVB200_F32 ? 2 : 1)) return 1;   // profiles/r02_small_n.jsonl: beyond, the large-N kernels win
+    const void* fn = v.fn[c->dtype == GRAVB200_F32 ? 0 : 1];
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, v.threads, g.smem));
+    if (occ < 1) return forced ? fail(GRAVB200_ECUDA, "variant %s does not fit on an SM", v.name) : 1;
+    if (!c->gbar) {
+        CU(cudaMalloc(&c->gbar, sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(c->gbar, 0, sizeof(unsigned long long), c->stream));
+        c->gbar_count = 0;
+    }
+    c->small_variant = sv; c->small_ng = g.ng; c->small_rpc = g.rpc; c->small_slice = g.slice; c->small_smem = g.smem;
+    c->grid = g.grid;
+    c->occ = occ;
+    c->use_small = true;
+    return 0;
+}
+
+int launch_small(gravb200_ctx* c, int k, int integrate) {
+    const SmallVariant& v = variants_small()[c->small_variant];
+    SmallParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.pos[0] = c->pos[0]; sp.pos[1] = c->pos[1];
+    sp.vel[0] = c->vel[0]; sp.vel[1] = c->vel[1];
+    sp.acc = c->acc;
+    sp.gbar = c->gbar;
+    sp.gbar_base = c->gbar_count;
+    sp.error = c->xerr;
+    sp.n = c->n_total;
+    sp.rpc = c->small_rpc; sp.ng = c->small_ng; sp.slice = c->small_slice;
+    sp.front = c->front;
+    sp.k = k;
+    sp.integrate = integrate;
+    sp.G = c->G; sp.T = c->T;
+    sp.eps2_f = (float)(c->eps * c->eps);
+    sp.eps2_d = c->eps * c->eps;
+    sp.clk = c->clk;
+    void* args[] = {&sp};
+    const void* fn = v.fn[c->dtype == GRAVB200_F32 ? 0 : 1];
+    if (k > 1) {   // the grid barrier needs every CTA resident: a cooperative launch guarantees it or fails
+        CU(cudaLaunchCooperativeKernel(fn, dim3(c->grid), dim3(v.threads), args, c->small_smem, c->stream));
+        c->gbar_count += (unsigned long long)c->grid * (unsigned long long)(k - 1);
+    } else {
+        CU(cudaLaunchKernel(fn, dim3(c->grid), dim3(v.threads), args, c->small_smem, c->stream));
+    }
+    c->launches++;
     return 0;
 }
 
 // CUDA graph of kGraphSteps (even: the front buffer is the same before and after) full steps.  Kernel
 // arguments depend only on the front-buffer parity, the variant and G/T/eps, so a graph stays valid until
 // one of those changes (pick_variant, upload).
+constexpr int kFlagsSweep = kMaxPeers + 1, kFlagsIntegrate = 2 * (kMaxPeers + 1), kFlagsTotal = 3 * (kMaxPeers + 1);
 constexpr int kGraphSteps = 8;
 constexpr int64_t kGraphMaxN = 32768;   // above, a step takes > 0.3 ms and launch latency is noise
 
@@ -434,6 +530,16 @@ void graph_invalidate(gravb200_ctx* c) {
 int pick_variant(gravb200_ctx* c) {
     graph_invalidate(c);
     c->use_sym = false;
+    c->use_small = false;
+    if (c->forced_variant >= kSmallBase) {
+        if (c->forced_variant - kSmallBase >= (int)variants_small().size()) return fail(GRAVB200_EINVAL, "variant %d out of range", c->forced_variant);
+        if (c->world != 1) return fail(GRAVB200_EINVAL, "the persistent small-N kernel runs on one shard only");
+        return setup_small(c, c->forced_variant - kSmallBase, true);
+    }
+    if (c->forced_variant < 0 && c->world == 1 && c->n_local > 0) {
+        const int rc = setup_small(c, 0, false);
+        if (rc <= 0) return rc;   // 0: chosen, < 0: CUDA error; 1: not eligible, go on
+    }
     // symmetric sweep: forced (ids >= kSymBase) or automatic once there are enough body-blocks.  Several
     // shards need the peer-store exchange (the owner of a row reads the other shards' partial sums over
     // NVLink) and block-aligned shards.
@@ -450,18 +556,11 @@ int pick_variant(gravb200_ctx* c) {
         int sv = -1;
         if (c->forced_variant >= kSymBase) sv = c->forced_variant - kSymBase;
         else if (c->forced_variant < 0 && c->n_total >= kSymShardMinN) {
-            // the fastest variant whose blocks the shards are whole multiples of (shard_chunk aligned them)
-            const SymChoice* ch = sym_shard_choices(c->dtype);
-            const SymVariant& v0 = variants_sym_of(c->dtype)[ch[0].variant];
-            sv = c->chunk % ((long long)v0.threads * v0.r) == 0 ? ch[0].variant : ch[1].variant;
+            // a shard does 1 / world of the universe's pairs: choose as one GPU would for a universe with that many
+            const double n_eff = (double)c->n_total / std::sqrt((double)c->world);
+            sv = c->dtype == GRAVB200_F32 ? (n_eff >= 65536 ? 0 : (n_eff >= 16384 ? 1 : 6)) : (n_eff >= 16384 ? 1 : 2);
         }
-        if (sv >= 0) {
-            const SymVariant& v = variants_sym_of(c->dtype)[sv];
-            const long long iblk = (long long)v.threads * v.r;
-            if (c->chunk % iblk == 0 && c->n_local > 0) return setup_sym(c, sv);
-            if (c->forced_variant >= kSymBase)
-                return fail(GRAVB200_EINVAL, "symmetric variant %s needs shards that are multiples of %lld rows", v.name, iblk);
-        }
+        if (sv >= 0) return setup_sym(c, sv);
     } else if (c->forced_variant >= kSymBase) {
         return fail(GRAVB200_EINVAL, "on several shards the symmetric variants need the peer-store exchange");
     }
@@ -527,28 +626,28 @@ int pick_variant(gravb200_ctx* c) {
 int peer_barrier(gravb200_ctx* c);
 
 int launch_sweep(gravb200_ctx* c, int integrate) {
-    if (c->n_local <= 0 || c->grid <= 0) return 0;
+    if (c->grid <= 0 || (c->n_local <= 0 && !(c->use_sym && c->world > 1))) return 0;
+    if (c->use_small) return launch_small(c, 1, integrate);
     if (c->use_sym) {
         const SymVariant& sv = variants_sym_of(c->dtype)[c->sym_variant];
+        const bool multi = c->world > 1;
         SymParams sp;
+        memset(&sp, 0, sizeof(sp));
         sp.pos_front = (const float4*)c->pos[c->front];
         sp.pos_front_d = (const double4*)c->pos[c->front];
         sp.eps2_d = c->eps * c->eps;
         sp.acc64 = c->acc64;
         sp.row_start = c->row_start;
         sp.n_total = c->n_total;
-        sp.row0 = c->row0;
-        sp.n_local = c->n_local;
+        sp.row0 = 0;                    // the flat list spans the universe; a shard takes items, not rows
+        sp.n_local = c->n_total;
         sp.n_iblocks = c->sym_blocks;
         sp.n_gblocks = c->sym_gblocks;
-        sp.gblock0 = (int)(c->row0 / ((long long)sv.threads * sv.r));
+        sp.gblock0 = 0;
         sp.eps2_f = (float)(c->eps * c->eps);
         sp.clk = c->clk;
-        void* sargs[] = {&sp};
-        const bool trace = c->world > 1 && c->tev[0];
-        if (trace) CU(cudaEventRecord(c->tev[0], c->stream));
-        CU(cudaLaunchKernel(sv.fn, dim3(c->grid), dim3(sv.threads), sargs, sv.smem, c->stream));
-        if (trace) CU(cudaEventRecord(c->tev[1], c->stream));
+        sp.item_lo = c->sym_lo;
+        sp.item_hi = c->sym_hi;
         IntegrateParams ip;
         memset(&ip, 0, sizeof(ip));
         ip.sp.pos_front = c->pos[c->front];
@@ -565,21 +664,43 @@ int launch_sweep(gravb200_ctx* c, int integrate) {
         ip.sp.n_peers = 0;
         ip.acc64 = c->acc64;
         ip.n_src = 0;
-        if (c->world > 1) {
-            // every shard's sweep must be complete before the owners read the partial sums
-            int rc = peer_barrier(c);
-            if (rc) return rc;
-            if (trace) CU(cudaEventRecord(c->tev[2], c->stream));
+        if (multi) {
+            // step generation e: the sweep starts once every shard's integrate of generation e - 1 is done (all r'
+            // have landed here, all rows of this accumulator are zero again) and publishes "sweep e done"; the
+            // integrate kernel starts once every shard has published that, adds the partial sums of all shards for
+            // the rows it owns over NVLink, stores r' to every peer and publishes "integrate e done".  No barrier
+            // launches, no memset: two kernels per step.
+            const unsigned long long e = ++c->sym_epoch;
+            PeerSync& a = sp.sync;
+            a.wait_flags = c->flags + kFlagsIntegrate;
+            a.wait_value = e - 1;
+            a.signal_value = e;
+            a.done_ctr = c->done_ctr;
+            a.rank = c->rank; a.world = c->world; a.error = c->xerr;
+            PeerSync& b = ip.sync;
+            b.wait_flags = c->flags + kFlagsSweep;
+            b.wait_value = e;
+            b.signal_value = e;
+            b.done_ctr = c->done_ctr + 1;
+            b.rank = c->rank; b.world = c->world; b.error = c->xerr;
             for (int q = 0; q < c->world; ++q) {
+                a.signal_flags[q] = c->peer_flags[q] + kFlagsSweep;
+                b.signal_flags[q] = c->peer_flags[q] + kFlagsIntegrate;
                 ip.acc_src[ip.n_src++] = c->peer_acc[q];
                 if (q != c->rank) ip.sp.peer_back[ip.sp.n_peers++] = c->peer_pos[c->front ^ 1][q];
             }
         }
-        const unsigned gb = (unsigned)((c->n_local + 255) / 256);
+        void* sargs[] = {&sp};
+        const bool trace = multi && c->tev[0];
+        if (trace) CU(cudaEventRecord(c->tev[0], c->stream));
+        CU(cudaLaunchKernel(sv.fn, dim3(c->grid), dim3(sv.threads), sargs, sv.smem, c->stream));
+        if (trace) CU(cudaEventRecord(c->tev[1], c->stream));
+        const unsigned gb = (unsigned)std::max<long long>(1, (c->n_local + 255) / 256);
         if (c->dtype == GRAVB200_F32) sym_integrate_kernel<float><<<gb, 256, 0, c->stream>>>(ip);
         else sym_integrate_kernel<double><<<gb, 256, 0, c->stream>>>(ip);
         CU(cudaGetLastError());
-        if (trace) CU(cudaEventRecord(c->tev[3], c->stream));
+        if (trace) CU(cudaEventRecord(c->tev[2], c->stream));
+        c->sym_tail_pending = multi;
         c->launches += 2;
         return 0;
     }
@@ -669,17 +790,29 @@ int check_barrier_error(gravb200_ctx* c) {
     return 0;
 }
 
-int exchange(gravb200_ctx* c) {
+// tail of a symmetric multi-shard step: wait (on the device) until every shard's integrate kernel is done, i.e.
+// all r' have landed in this GPU's back buffer.  Between consecutive steps of gravb200_steps the next sweep does
+// this wait itself; the host needs it before it looks at the state (stage2, end of steps).
+int sym_tail_wait(gravb200_ctx* c) {
+    if (!c->sym_tail_pending) return 0;
+    PeerSync w;
+    memset(&w, 0, sizeof(w));
+    w.wait_flags = c->flags + kFlagsIntegrate;
+    w.wait_value = c->sym_epoch;
+    w.rank = c->rank; w.world = c->world; w.error = c->xerr;
+    peer_wait_kernel<<<1, 32, 0, c->stream>>>(w);
+    CU(cudaGetLastError());
+    c->launches++;
+    c->sym_tail_pending = false;
+    if (c->tev[0]) { CU(cudaEventRecord(c->tev[3], c->stream)); c->tev_ok = true; }
+    return 0;
+}
+
+int exchange(gravb200_ctx* c, bool last = true) {
     if (c->world == 1) return 0;
-    if (c->peer_mode) {   // the data already travelled in the sweep's epilogue
-        int rc = peer_barrier(c);
-        if (rc) return rc;
-        const bool trace = c->use_sym && c->tev[0];
-        if (trace) CU(cudaEventRecord(c->tev[4], c->stream));
-        // symmetric sweep: all owners have read this shard's partial sums; clear them for the next step
-        if (c->use_sym) CU(cudaMemsetAsync(c->acc64, 0, (size_t)c->n_pad * 4 * sizeof(double), c->stream));
-        if (trace) { CU(cudaEventRecord(c->tev[5], c->stream)); c->tev_ok = true; }
-        return 0;
+    if (c->peer_mode) {   // the data already travelled in the sweep's epilogue / the integrate kernel
+        if (c->use_sym) return last ? sym_tail_wait(c) : 0;
+        return peer_barrier(c);
     }
     char* back = (char*)c->pos[c->front ^ 1];
     const size_t count = (size_t)c->chunk * 4;   // scalars per shard
@@ -688,17 +821,16 @@ int exchange(gravb200_ctx* c) {
     return 0;
 }
 
-// An upload replaces the state a pending stage1 was computed from: the step is dropped.  On several shards
-// the symmetric sweep has left partial sums in the accumulator (one shard: the integrate kernel cleared
-// it; several: the clear belongs to the exchange that will not happen).
+// An upload replaces the state a pending stage1 was computed from: the step is dropped.
 int drop_pending(gravb200_ctx* c) {
     if (c->pending && c->use_sym && c->world > 1 && c->acc64) {
-        // the owners may still be reading this shard's partial sums (integrate kernel of the dropped step):
-        // same order as a regular exchange — step barrier first, then the clear.  Every rank drops the step
-        // (uploads and repeated stage1 calls are collective), so the barrier generations stay in lockstep.
-        int rc = peer_barrier(c);
+        // the dropped step ran sweep + integrate everywhere (the integrate kernels zeroed the accumulators again);
+        // what follows may overwrite positions the peers still read, so all shards meet first.  Every rank drops
+        // the step (uploads and repeated stage1 calls are collective): the generations stay in lockstep.
+        int rc = sym_tail_wait(c);
         if (rc) return rc;
-        CU(cudaMemsetAsync(c->acc64, 0, (size_t)c->n_pad * 4 * sizeof(double), c->stream));
+        rc = peer_barrier(c);
+        if (rc) return rc;
     }
     c->pending = false;
     return 0;
@@ -913,12 +1045,29 @@ int gravb200_sym_variant_count(int dtype) {
     return (int)variants_sym_of(dtype).size();
 }
 
+int gravb200_small_variant_count(void) { return (int)variants_small().size(); }
+
+int gravb200_small_geometry(int64_t n_total, int dtype, int sm_count, int variant, int64_t* out, int n) {
+    if (!out || n < 6) return fail(GRAVB200_EINVAL, "out needs room for 6 values");
+    if (dtype != GRAVB200_F32 && dtype != GRAVB200_F64) return fail(GRAVB200_EINVAL, "unknown dtype %d", dtype);
+    if (variant < kSmallBase || variant - kSmallBase >= (int)variants_small().size()) return fail(GRAVB200_EINVAL, "variant %d is not a persistent small-N kernel", variant);
+    if (n_total < 1 || sm_count < 1) return fail(GRAVB200_EINVAL, "n_total and sm_count must be >= 1");
+    SmallGeometry g;
+    memset(&g, 0, sizeof(g));
+    const int fit = small_geometry(n_total, dtype, sm_count, variants_small()[variant - kSmallBase], &g);
+    if (fit == 1) return fail(GRAVB200_EINVAL, "%lld bodies need more rows per CTA than the variant has lanes for", (long long)n_total);
+    const int64_t t[6] = {g.grid, g.rpc, g.ng, g.slice, g.nsl, (int64_t)g.smem};
+    memcpy(out, t, sizeof(t));
+    return fit == 2 ? 1 : 0;
+}
+
 int gravb200_variant_count(int dtype) {
     if (dtype != GRAVB200_F32 && dtype != GRAVB200_F64) return 0;
     return (int)variants_of(dtype).size();
 }
 const char* gravb200_variant_name(int dtype, int variant) {
     if (dtype != GRAVB200_F32 && dtype != GRAVB200_F64) return "";
+    if (variant >= kSmallBase) return variant - kSmallBase < (int)variants_small().size() ? variants_small()[variant - kSmallBase].name : "";
     if (variant >= kSymBase && variant - kSymBase < (int)variants_sym_of(dtype).size())
         return variants_sym_of(dtype)[variant - kSymBase].name;
     const auto& vs = variants_of(dtype);
@@ -995,8 +1144,10 @@ int gravb200_ctx_create(int64_t n_total, int dtype, int device, int rank, int wo
     CUX(cudaMalloc(&c->stage3, (size_t)n_total * 3 * c->esz));
     CUX(cudaMalloc(&c->stagem, (size_t)n_total * c->esz));
     CUX(cudaMalloc(&c->clk, 2048 * sizeof(unsigned long long)));   // [0..1] CTA 0 cycles/ns, then per-CTA start/end stamps
-    CUX(cudaMalloc(&c->flags, (kMaxPeers + 1) * sizeof(unsigned long long)));
-    CUX(cudaMemsetAsync(c->flags, 0, (kMaxPeers + 1) * sizeof(unsigned long long), c->stream));
+    CUX(cudaMalloc(&c->flags, kFlagsTotal * sizeof(unsigned long long)));
+    CUX(cudaMemsetAsync(c->flags, 0, kFlagsTotal * sizeof(unsigned long long), c->stream));
+    CUX(cudaMalloc(&c->done_ctr, 2 * sizeof(unsigned int)));
+    CUX(cudaMemsetAsync(c->done_ctr, 0, 2 * sizeof(unsigned int), c->stream));
     if (world > 1) {   // symmetric sweep accumulator: must exist before peer_export
         CUX(cudaMalloc(&c->acc64, (size_t)c->n_pad * 4 * sizeof(double)));
         CUX(cudaMemsetAsync(c->acc64, 0, (size_t)c->n_pad * 4 * sizeof(double), c->stream));
@@ -1046,9 +1197,11 @@ int gravb200_ctx_destroy(gravb200_ctx* c) {
         if (c->peer_acc[q]) cudaIpcCloseMemHandle(c->peer_acc[q]);
     }
     if (c->flags) cudaFree(c->flags);
+    if (c->done_ctr) cudaFree(c->done_ctr);
     if (c->acc64) cudaFree(c->acc64);
     if (c->row_start) cudaFree(c->row_start);
     if (c->xerr) cudaFree(c->xerr);
+    if (c->gbar) cudaFree(c->gbar);
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->tev)
@@ -1178,7 +1331,16 @@ int gravb200_steps(gravb200_ctx* c, int k) {
     if (rc0) return rc0;
     CU(cudaEventRecord(c->ev[0], c->stream));
     int s = 0;
-    if (c->world == 1 && c->n_total <= kGraphMaxN && c->n_local > 0) {
+    if (c->use_small && c->n_local > 0) {
+        // all k steps in ONE cooperative launch (grid barrier between steps), in chunks that keep a launch finite
+        for (; s < k;) {
+            const int kk = std::min(k - s, 1 << 16);
+            int rc = launch_small(c, kk, 1);
+            if (rc) return rc;
+            if (kk & 1) c->front ^= 1;
+            s += kk;
+        }
+    } else if (c->world == 1 && c->n_total <= kGraphMaxN && c->n_local > 0) {
         // launch-bound sizes: whole groups of kGraphSteps steps go out as one graph launch each
         for (; k - s >= kGraphSteps; s += kGraphSteps) {
             cudaGraphExec_t ex = nullptr;
@@ -1191,7 +1353,7 @@ int gravb200_steps(gravb200_ctx* c, int k) {
     for (; s < k; ++s) {
         int rc = launch_sweep(c, 1);
         if (rc) return rc;
-        rc = exchange(c);
+        rc = exchange(c, s == k - 1);   // symmetric sweep on several shards: the next sweep waits for the peers itself
         if (rc) return rc;
         c->front ^= 1;
     }
@@ -1199,6 +1361,11 @@ int gravb200_steps(gravb200_ctx* c, int k) {
     CU(cudaStreamSynchronize(c->stream));
     c->ev_sweep = false;
     c->ev_steps = true;
+    if (c->use_small && k > 1) {
+        int e = 0;
+        CU(cudaMemcpy(&e, c->xerr, sizeof(int), cudaMemcpyDeviceToHost));
+        if (e) return fail(GRAVB200_ECUDA, "persistent step kernel: a CTA did not reach the grid barrier within 20 s");
+    }
     return check_barrier_error(c);
 }
 
@@ -1245,8 +1412,8 @@ int gravb200_timings(gravb200_ctx* c, float* ms, int n) {
         CU(cudaMemcpy(h, c->clk, sizeof(h), cudaMemcpyDeviceToHost));
         ms[3] = h[1] ? (float)((double)h[0] / (double)h[1] * 1e3) : -1.f;   // cycles/ns -> MHz
         if (n > 4) ms[4] = (float)((double)h[1] * 1e-6);   // lifetime of CTA 0 of the last sweep, ms
-        if (n > 9 && c->tev_ok && c->use_sym && c->world > 1 && cudaEventQuery(c->tev[5]) == cudaSuccess)
-            for (int i = 0; i < 5; ++i) CU(cudaEventElapsedTime(&ms[5 + i], c->tev[i], c->tev[i + 1]));
+        if (n > 7 && c->tev_ok && c->use_sym && c->world > 1 && cudaEventQuery(c->tev[3]) == cudaSuccess)
+            for (int i = 0; i < 3; ++i) CU(cudaEventElapsedTime(&ms[5 + i], c->tev[i], c->tev[i + 1]));
 #ifdef SYM_DEBUG
         if (n > 16) {   // [2036..2046] divergence counters of SYM_DIVCHK, [2047] cycles spent in jbar waits
             unsigned long long d[12];
@@ -1263,7 +1430,12 @@ int gravb200_timings(gravb200_ctx* c, float* ms, int n) {
 int gravb200_info(const gravb200_ctx* c, int64_t* info, int n) {
     if (!c || !info) return fail(GRAVB200_EINVAL, "ctx / info is NULL");
     int64_t vals[12];
-    if (c->use_sym) {
+    if (c->use_small) {
+        const SmallVariant& v = variants_small()[c->small_variant];
+        const int64_t t[12] = {c->grid, v.threads, v.r, c->small_slice, 1, (int64_t)c->small_smem,
+                               c->launches, c->sm_count, 1, c->occ, 0, kSmallBase + c->small_variant};
+        memcpy(vals, t, sizeof(t));
+    } else if (c->use_sym) {
         const SymVariant& v = variants_sym_of(c->dtype)[c->sym_variant];
         const int64_t t[12] = {c->grid, v.threads, v.r, v.tile, v.stages, (int64_t)v.smem,
                                c->launches, c->sm_count, 1, c->occ, c->peer_mode ? 1 : 0, kSymBase + c->sym_variant};
@@ -1280,7 +1452,9 @@ int gravb200_info(const gravb200_ctx* c, int64_t* info, int n) {
 
 int gravb200_set_variant(gravb200_ctx* c, int variant) {
     if (!c) return fail(GRAVB200_EINVAL, "ctx is NULL");
-    if (variant >= kSymBase) {
+    if (variant >= kSmallBase) {
+        if (variant - kSmallBase >= (int)variants_small().size()) return fail(GRAVB200_EINVAL, "variant %d out of range", variant);
+    } else if (variant >= kSymBase) {
         if (variant - kSymBase >= (int)variants_sym_of(c->dtype).size()) return fail(GRAVB200_EINVAL, "variant %d out of range", variant);
     } else if (variant >= (int)variants_of(c->dtype).size()) return fail(GRAVB200_EINVAL, "variant %d out of range", variant);
     if (c->pending) return fail(GRAVB200_EINVAL, "cannot switch variant between stage1 and stage2");

@@ -149,6 +149,71 @@ __host__ __device__ __forceinline__ long long sk_owner(long long total, long lon
     return ((t + 1) * S - 1) / total;
 }
 
+__device__ __forceinline__ void fence_proxy_async_all() {
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross-GPU hand-over folded INTO the compute kernels of the symmetric multi-shard step (no barrier launches):
+// a kernel may begin by waiting until every peer has published `wait_value` in this GPU's flag array
+// (peer_wait), and end by publishing `signal_value` into every peer's flag array once ALL its CTAs are done
+// (peer_signal: per-kernel arrival counter, the last CTA releases the flags at system scope).  The sweep waits
+// for "integrate of the previous step finished everywhere" and signals "my sweep is done"; the integrate
+// kernel waits for that and signals "my integrate is done" — so the exchange of step s overlaps whatever the
+// peers are still doing, and consecutive steps need two launches each.
+// ------------------------------------------------------------------------------------------------
+struct PeerSync {
+    const unsigned long long* wait_flags;             // local [world], written by the peers; nullptr: no wait
+    unsigned long long wait_value;
+    unsigned long long* signal_flags[kMaxPeers + 1];  // flag arrays of all ranks (entry [rank] of each is ours)
+    unsigned long long signal_value;
+    unsigned int* done_ctr;                           // CTAs of this launch that are done (self-resetting); nullptr: no signal
+    int rank, world;
+    int* error;                                       // set to 1 when a peer does not show up within 60 s
+};
+
+// all threads of the CTA call it; returns after a CTA barrier.  Warp 0 polls (lane q watches peer q) and leaves
+// the loop on a vote, so no warp is ever split by the wait.
+__device__ __forceinline__ void peer_wait(const PeerSync& s) {
+    if (threadIdx.x < 32) {
+        const int q = threadIdx.x;
+        const bool mine = q < s.world && q != s.rank;
+        unsigned long long t0, t1, seen;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        bool ok;
+        do {
+            ok = true;
+            if (mine) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(s.wait_flags + q) : "memory");
+                ok = seen >= s.wait_value;
+                if (!ok) {
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > 60ull * 1000 * 1000 * 1000) { *s.error = 1; ok = true; }
+                }
+            }
+        } while (!__all_sync(0xffffffffu, ok ? 1 : 0));
+    }
+    __syncthreads();
+    fence_proxy_async_all();   // what the peers stored is read by TMA bulk copies (async proxy) too
+}
+
+// all threads of the CTA call it, after their last store of the launch
+__device__ __forceinline__ void peer_signal(const PeerSync& s) {
+    if (s.done_ctr == nullptr) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned int old = atomicAdd(s.done_ctr, 1u);
+        if (old == gridDim.x - 1) {
+            *s.done_ctr = 0;   // the next launch that uses it is stream-ordered behind this one
+            __threadfence_system();   // fence + relaxed stores = one release for all peers (a st.release each would fence again)
+            for (int q = 0; q < s.world; ++q)
+                if (q != s.rank)
+                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(s.signal_flags[q] + s.rank), "l"(s.signal_value) : "memory");
+        }
+    }
+}
+
 template <typename T> struct Vec4;
 template <> struct Vec4<float> { using type = float4; };
 template <> struct Vec4<double> { using type = double4; };
@@ -602,5 +667,9 @@ __global__ void exchange_barrier_kernel(const BarrierParams b) {
     } while (t1 - t0 < b.timeout_ns);
     *b.error = 1;
 }
+
+// Tail of a symmetric multi-shard step when the host wants the state complete (stage2, last step of steps(k)):
+// every peer has finished its integrate kernel, i.e. all r' have landed here.
+__global__ void peer_wait_kernel(const PeerSync s) { peer_wait(s); }
 
 }  // namespace gravb200

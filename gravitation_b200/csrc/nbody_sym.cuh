@@ -56,6 +56,11 @@ struct SymParams {
     float eps2_f;
     double eps2_d;
     unsigned long long* clk;
+    // this launch's share of the flat (row, tile) list: [item_lo, item_hi).  One shard: everything.  Several
+    // shards: the GLOBAL list (n_iblocks = n_gblocks, gblock0 = 0, row0 = 0, n_local = n_total) is cut into one
+    // equal range per shard — stream-K across GPUs, whatever the row ownership of the integrate step is.
+    long long item_lo, item_hi;
+    PeerSync sync;                // several shards: hand-over with the peers' integrate kernels (nbody_kernels.cuh)
 };
 
 // geometry helpers shared by host and device ---------------------------------------------------------
@@ -117,10 +122,10 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
     float* jpart = reinterpret_cast<float*>(ssum + (size_t)3 * R * THREADS);       // [2][NWARPS][3][TILE]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long total = p.row_start[p.n_iblocks];
+    const long long total = p.item_hi - p.item_lo;
     const long long S = gridDim.x;
-    const long long lo = sk_lo(total, blockIdx.x, S), hi = sk_lo(total, blockIdx.x + 1, S);
-    if (lo >= hi) return;
+    const long long lo = p.item_lo + sk_lo(total, blockIdx.x, S), hi = p.item_lo + sk_lo(total, blockIdx.x + 1, S);
+    if (lo >= hi) { peer_signal(p.sync); return; }   // CTA-uniform; an idle CTA still counts as done
     const int ntiles = (int)(hi - lo);
 
     if (tid == 0) {
@@ -129,6 +134,9 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
         mbar_fence_init();
     }
     __syncthreads();
+    // several shards: the peers' integrate kernels of the previous step have stored their r' into this GPU's
+    // position buffer and zeroed their rows of this GPU's accumulator — only then may this sweep read / add
+    if (p.sync.wait_flags) peer_wait(p.sync);
 
     unsigned long long clk0 = 0, ns0 = 0;
     if (p.clk && tid == 0) {   // every CTA: start/end time stamps (debug: distribution of CTA lifetimes)
@@ -413,6 +421,7 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
         if (blockIdx.x == 0) { p.clk[0] = clock64() - clk0; p.clk[1] = ns1 - ns0; }
         if (blockIdx.x < 1016) { p.clk[2 + 2 * blockIdx.x] = ns0; p.clk[3 + 2 * blockIdx.x] = ns1; }
     }
+    peer_signal(p.sync);   // several shards: "my sweep is done" once every CTA has got here
 }
 
 template <int THREADS, int R, int TILE, int STAGES>
@@ -446,10 +455,10 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
     double* jpart = reinterpret_cast<double*>(jbar + 1);             // [2][NWARPS][3][TILE]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long total = p.row_start[p.n_iblocks];
+    const long long total = p.item_hi - p.item_lo;
     const long long S = gridDim.x;
-    const long long lo = sk_lo(total, blockIdx.x, S), hi = sk_lo(total, blockIdx.x + 1, S);
-    if (lo >= hi) return;
+    const long long lo = p.item_lo + sk_lo(total, blockIdx.x, S), hi = p.item_lo + sk_lo(total, blockIdx.x + 1, S);
+    if (lo >= hi) { peer_signal(p.sync); return; }   // CTA-uniform; an idle CTA still counts as done
     const int ntiles = (int)(hi - lo);
 
     if (tid == 0) {
@@ -458,6 +467,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
         mbar_fence_init();
     }
     __syncthreads();
+    if (p.sync.wait_flags) peer_wait(p.sync);   // as in the fp32 kernel
 
     unsigned long long clk0 = 0, ns0 = 0;
     if (p.clk && blockIdx.x == 0 && tid == 0) {
@@ -660,6 +670,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
         p.clk[0] = clock64() - clk0;
         p.clk[1] = ns1 - ns0;
     }
+    peer_signal(p.sync);
 }
 
 template <int THREADS, int TILE, int STAGES>
@@ -676,32 +687,46 @@ struct IntegrateParams {
     SweepParams sp;      // pos/vel/acc buffers, G, T, row0, n_local, peers
     double* acc64;       // [n_pad][4] this shard's accumulator
     // several shards: every shard accumulated partial sums for ALL bodies; the owner of a row adds the
-    // partials of all shards in rank order (own memory + NVLink peer loads) — a reduce-scatter fused into
-    // the integrate kernel.  n_src == 0: single shard, read and clear acc64.
+    // partials of all shards in rank order (own memory + NVLink peer loads, all in flight at once) and zeroes
+    // them for the next step — a reduce-scatter fused into the integrate kernel.  n_src == 0: single shard.
     int n_src;
-    const double* acc_src[kMaxPeers + 1];
+    double* acc_src[kMaxPeers + 1];
+    PeerSync sync;       // several shards: wait for every shard's sweep, then tell the peers "my integrate is done"
 };
 
 template <typename REAL>
 __global__ void sym_integrate_kernel(const IntegrateParams q) {
     using V4 = typename Vec4<REAL>::type;
     const long long il = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (il >= q.sp.n_local) return;
-    double sx, sy, sz;
-    if (q.n_src == 0) {
-        double4* src = reinterpret_cast<double4*>(q.acc64) + (q.sp.row0 + il);
-        const double4 s = *src;
-        *src = make_double4(0.0, 0.0, 0.0, 0.0);
-        sx = s.x; sy = s.y; sz = s.z;
-    } else {
-        sx = sy = sz = 0.0;
-        for (int r = 0; r < q.n_src; ++r) {   // the accumulators are cleared after the step barrier (host side)
-            const double4 s = ld_cg_d4(reinterpret_cast<const double4*>(q.acc_src[r]) + (q.sp.row0 + il));
-            sx += s.x; sy += s.y; sz += s.z;
+    if (q.sync.wait_flags) peer_wait(q.sync);   // every shard's sweep of this step is complete
+    if (il < q.sp.n_local) {
+        double sx, sy, sz;
+        if (q.n_src == 0) {
+            double4* src = reinterpret_cast<double4*>(q.acc64) + (q.sp.row0 + il);
+            const double4 s = *src;
+            *src = make_double4(0.0, 0.0, 0.0, 0.0);
+            sx = s.x; sy = s.y; sz = s.z;
+        } else {
+            sx = sy = sz = 0.0;
+            constexpr int B = 8;   // sources in flight per batch (one NVLink round trip per batch, not per source)
+            for (int r0 = 0; r0 < q.n_src; r0 += B) {
+                double4 part[B];
+#pragma unroll
+                for (int u = 0; u < B; ++u)
+                    if (r0 + u < q.n_src) part[u] = ld_cg_d4(reinterpret_cast<const double4*>(q.acc_src[r0 + u]) + (q.sp.row0 + il));
+#pragma unroll
+                for (int u = 0; u < B; ++u)
+                    if (r0 + u < q.n_src) {
+                        sx += part[u].x; sy += part[u].y; sz += part[u].z;   // rank order
+                        double2* z = reinterpret_cast<double2*>(reinterpret_cast<double4*>(q.acc_src[r0 + u]) + (q.sp.row0 + il));
+                        z[0] = make_double2(0.0, 0.0); z[1] = make_double2(0.0, 0.0);   // ready for the next sweep (peer store)
+                    }
+            }
         }
+        const V4 ri = reinterpret_cast<const V4*>(q.sp.pos_front)[q.sp.row0 + il];
+        finalize_body(q.sp, il, sx, sy, sz, ri, REAL(0));
     }
-    const V4 ri = reinterpret_cast<const V4*>(q.sp.pos_front)[q.sp.row0 + il];
-    finalize_body(q.sp, il, sx, sy, sz, ri, REAL(0));
+    peer_signal(q.sync);
 }
 
 }  // namespace gravb200

@@ -6,8 +6,8 @@ libgravb200 on its own stream (NCCL all-gather over NVLink).  torch.distributed 
 rendezvous (unique-id broadcast, barriers, max-over-ranks timing) and for gathering per-shard rows
 (velocities, accelerations) onto every rank when a caller asks for them.
 
-Row partition = SURVEY.md section 8e: contiguous slices of ceil(N / P) rows (rounded up to whole body-blocks
-of the symmetric sweep for large N), the last one short; the library is the single source of it."""
+Row partition = SURVEY.md section 8e: contiguous slices of ceil(N / P) rows,
+the last one short; the library is the single source of it."""
 
 import os
 
@@ -16,7 +16,7 @@ import numpy as np
 
 def row_partition(n, world, dtype = 'float32'):
 	"""[(row0, n_local)] per rank, asked from the library so that it IS the partition gravb200_ctx_create
-	applies (csrc/gravb200.cu shard_chunk: ceil(n / world) rows, block-aligned for large universes)"""
+	applies (csrc/gravb200.cu shard_chunk: ceil(n / world) rows, the last slice short)"""
 	from . import _shim
 	return _shim.partition(n, world, dtype)
 

@@ -109,18 +109,19 @@ int gravb200_sync(gravb200_ctx* ctx);
 int gravb200_download(gravb200_ctx* ctx, void* r, void* v, void* a);
 int gravb200_shard(const gravb200_ctx* ctx, int64_t* row0, int64_t* n_local);
 /* The row partition gravb200_ctx_create applies, without a context or a device (hosts that lay out their
- * mirrors before creating shards): contiguous slices of ceil(n_total / world) rows — for n_total >= 32768
- * rounded up to whole body-blocks of a symmetric sweep variant when the predicted step time is shorter
- * than with the ordered sweep on the plain partition — the last slice short (never empty for
- * n_total >= 32768; empty slices only when n_total < world). */
+ * mirrors before creating shards): contiguous slices of ceil(n_total / world) rows, the last slice short
+ * (slices are empty only when n_total is small against world).  The rows a shard owns are the
+ * rows it integrates; the symmetric sweep's WORK is divided independently of them (equal shares of the flat
+ * tile list of the whole universe), so no block alignment is involved. */
 int gravb200_partition(int64_t n_total, int dtype, int world, int rank, int64_t* row0, int64_t* n_local);
 
 /* Device-side timings (cudaEvent): ms[0] = last stage1 sweep kernel, ms[1] = last exchange,
  * ms[2] = total of the last gravb200_steps() call, ms[3] = SM clock (MHz) that CTA 0 of the last sweep
  * observed over its lifetime (clock64 / globaltimer), ms[4] = that lifetime in ms; several shards with the
- * symmetric sweep, last complete step: ms[5] = sweep kernel, ms[6] = wait for all shards' sweeps (flag barrier),
- * ms[7] = integrate kernel (peer loads of the partial sums + peer stores of r'), ms[8] = step barrier,
- * ms[9] = accumulator clear; entries that do not apply are -1; n = capacity of ms. */
+ * symmetric sweep, last step that was followed by stage2 / ended a gravb200_steps call: ms[5] = sweep kernel,
+ * ms[6] = integrate kernel (begins by waiting for every shard's sweep; peer loads of the partial sums, peer
+ * stores of r' and of the cleared sums), ms[7] = tail wait for every shard's integrate; entries that do not
+ * apply are -1; n = capacity of ms. */
 int gravb200_timings(gravb200_ctx* ctx, float* ms, int n);
 
 /* Introspection used by bench.py / tests: launch geometry and counters.
@@ -130,10 +131,19 @@ int gravb200_timings(gravb200_ctx* ctx, float* ms, int n);
 int gravb200_info(const gravb200_ctx* ctx, int64_t* info, int n);
 /* Force a kernel variant (tests / ncu A-B): variant < 0 restores the automatic choice.  Ids 0 .. count-1 are
  * the ordered sweeps (bit-reproducible), ids 100 + k, k < gravb200_sym_variant_count(dtype), the symmetric sweeps
- * (every unordered pair once, fp64 atomics: reproducible up to fp64 rounding of the cross-tile sum). */
+ * (every unordered pair once, fp64 atomics: reproducible up to fp64 rounding of the cross-tile sum), ids 200 + k,
+ * k < gravb200_small_variant_count(), the persistent multi-step kernel for universes that fit one SM's shared
+ * memory (one shard, bit-reproducible; the automatic choice up to 64 rows per SM, ~9 400 bodies on a B200 —
+ * there gravb200_steps(k) is ONE cooperative launch with a grid barrier between the steps). */
 int gravb200_set_variant(gravb200_ctx* ctx, int variant);
 int gravb200_variant_count(int dtype);
 int gravb200_sym_variant_count(int dtype);
+int gravb200_small_variant_count(void);
+/* Geometry the persistent kernel `variant` (>= 200) would run `n_total` bodies with on a device of `sm_count`
+ * SMs (needs no device): out[0]=CTAs, [1]=rows per CTA, [2]=row groups of 32 per CTA, [3]=j-slots per slice,
+ * [4]=slices, [5]=dynamic shared memory in bytes.  Returns 0 if it fits, 1 if the positions do not fit in
+ * shared memory, < 0 on bad arguments or too many rows per CTA. */
+int gravb200_small_geometry(int64_t n_total, int dtype, int sm_count, int variant, int64_t* out, int n);
 const char* gravb200_variant_name(int dtype, int variant);
 
 /* Raw device pointers of the shard state (for peer access / torch interop in tests).

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Dev tool: run `reps` stage1+stage2 steps of one variant (ncu target). usage: run_sweep.py N dtype variant reps"""
+"""Dev tool: run `reps` stage1+stage2 steps of one variant, then one steps(reps) call (ncu target).
+usage: run_sweep.py N dtype variant reps"""
 import sys, os, json
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -15,5 +16,7 @@ best = 1e30
 for _ in range(reps):
     sh.stage1(); sh.stage2()
     t = sh.timings(); best = min(best, t['sweep_ms'])
-print(json.dumps(dict(n=n, dtype=dtype, variant=('auto' if variant < 0 else _shim.sym_variant_names(dtype)[variant - _shim.SYM_BASE] if variant >= _shim.SYM_BASE else _shim.variant_names(dtype)[variant]), best_ms=best,
+sh.steps(reps)
+steps_ms = sh.timings()['steps_ms'] / reps
+print(json.dumps(dict(n=n, dtype=dtype, variant=variant, best_ms=best, steps_ms_per_step=steps_ms,
     tera_inter_s=n * (n - 1) / best / 1e9, sm_mhz=t['sm_mhz'], info=sh.info())))

@@ -37,7 +37,7 @@ def _worker(rank, world, port, n, out_dir):
 	tdist.destroy_process_group()
 
 
-@pytest.mark.parametrize('n', (10, 7, 1, 1 << 18)) # 2^18: block-aligned shards (132096 + 130048 rows)
+@pytest.mark.parametrize('n', (10, 7, 1, 1 << 18)) # 2^18: a size the symmetric sweep runs on several shards
 def test_two_rank_gloo_plumbing(n, tmp_path, shim):
 	import torch.multiprocessing as mp
 	port = _free_port()

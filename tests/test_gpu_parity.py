@@ -114,6 +114,8 @@ def test_every_kernel_variant_agrees_with_the_oracle(dtype, oracle, gpu):
 	ids = [(vi, name) for vi, name in enumerate(gpu.variant_names(dtype))]
 	# the symmetric sweeps (every unordered pair once) have ids SYM_BASE + k
 	ids += [(gpu.SYM_BASE + k, name) for k, name in enumerate(gpu.sym_variant_names(dtype))]
+	# the persistent multi-step kernels for small universes have ids SMALL_BASE + k
+	ids += [(gpu.SMALL_BASE + k, name) for k, name in enumerate(gpu.small_variant_names())]
 	for vi, name in ids:
 		a, info = run_stage1(gpu, r, v, m, G, T, dtype, variant = vi)
 		assert oracle.max_rel_err(a, ref) <= TOL_ACC[dtype], name
@@ -187,11 +189,15 @@ def test_steps_equals_repeated_stage_calls_and_is_deterministic(dtype, oracle, g
 
 
 @pytest.mark.parametrize('dtype', DTYPES)
-@pytest.mark.parametrize('n,variant', ((700, -1), (2048 + 77, 1), (9000, -1)))
+@pytest.mark.parametrize('n,variant', ((700, -1), (700, 3), (2048 + 77, 1), (9000, -1), (9000, 102), (12000, -1)))
 def test_graph_replayed_steps_equal_single_steps(n, variant, dtype, oracle, gpu):
-	"""steps(k) replays groups of 8 steps from a CUDA graph on launch-bound sizes (plus single launches for the
-	remainder); the state must equal k stage1()+stage2() calls — bit for bit with the ordered sweeps, to fp64
-	rounding of the accumulator with the symmetric one (n = 9000) — also after a re-upload with another T"""
+	"""steps(k) is ONE cooperative launch of the persistent kernel for small universes (automatic choice up to
+	~9 400 bodies) and replays groups of 8 steps from a CUDA graph on the other launch-bound sizes (plus single
+	launches for the remainder); the state must equal k stage1()+stage2() calls — bit for bit with the persistent
+	kernel and the ordered sweeps, to fp64 rounding of the accumulator with the symmetric ones — also after a
+	re-upload with another T"""
+	if variant == 3 and dtype == 'float64':
+		variant = 2
 	r, v, m, G, T = oracle.uniform_universe(n, 33, dtype)
 	for t_step, k in ((T, 19), (T * 0.5, 8)):
 		outs = []
@@ -209,9 +215,16 @@ def test_graph_replayed_steps_equal_single_steps(n, variant, dtype, oracle, gpu)
 					sh.stage1(); sh.stage2()
 			else:
 				sh.steps(k)
-			assert sh.info()['launches'] - launches0 == k * (2 if sh.info()['variant'] >= gpu.SYM_BASE else 1)
+			vid = sh.info()['variant']
+			symmetric = gpu.SYM_BASE <= vid < gpu.SMALL_BASE
+			small_range = n <= 9472 and gpu.small_geometry(n, dtype, sh.info()['sm_count'])['fits'] # fp64: 32 bytes per body
+			if vid >= gpu.SMALL_BASE:
+				assert variant < 0 and small_range
+				assert sh.info()['launches'] - launches0 == (k if mode == 'stages' else 1)
+			else:
+				assert variant >= 0 or not small_range
+				assert sh.info()['launches'] - launches0 == k * (2 if symmetric else 1)
 			outs.append(sh.download(a = True))
-			symmetric = sh.info()['variant'] >= gpu.SYM_BASE
 			sh.close()
 		for x, y in zip(*outs):
 			if symmetric:
@@ -275,7 +288,7 @@ def test_full_size_properties(dtype, n, oracle, gpu):
 	sh.upload(r, v, (m * 2).astype(dtype), G, T)
 	sh.stage1(); sh.sync()
 	_, _, a_m2 = sh.download(r = False, v = False, a = True)
-	if sh.info()['variant'] >= gpu.SYM_BASE:
+	if gpu.SYM_BASE <= sh.info()['variant'] < gpu.SMALL_BASE:
 		assert oracle.max_rel_err(a_m2, a.astype(np.float64) * 2.0) <= (3e-7 if dtype == 'float32' else 1e-12) # per body, vector norm
 	else:
 		assert np.array_equal(a_m2, a * np.array(2, dtype))
@@ -448,9 +461,9 @@ def test_accuracy_command_float32_against_float64(gpu):
 
 
 @pytest.mark.parametrize('dtype', DTYPES)
-@pytest.mark.parametrize('n', (8192, 10007, 40000))
+@pytest.mark.parametrize('n', (9473, 10007, 40000))
 def test_symmetric_sweep_parity_and_reproducibility(n, dtype, oracle, gpu):
-	"""the default fp32 path from N = 8192 on: every unordered pair once (nbody_sym.cuh).  Parity against
+	"""the default path above the persistent small-N kernel's range (N > 9472 on 148 SMs): every unordered pair once (nbody_sym.cuh).  Parity against
 	the float64 oracle, bit-exact stage 2, and run-to-run agreement (fp64 atomics: reproducible up to the
 	rounding of the cross-tile fp64 sum, far below float32 resolution)"""
 	r, v, m, G, T = oracle.uniform_universe(n, 77, dtype)
@@ -460,7 +473,7 @@ def test_symmetric_sweep_parity_and_reproducibility(n, dtype, oracle, gpu):
 	for _ in range(2):
 		sh = gpu.Shard(n, dtype)
 		sh.upload(r, v, m, G, T)
-		assert sh.info()['variant'] >= gpu.SYM_BASE
+		assert gpu.SYM_BASE <= sh.info()['variant'] < gpu.SMALL_BASE
 		sh.stage1(); sh.stage2()
 		outs.append(sh.download(a = True))
 		sh.close()
@@ -470,6 +483,52 @@ def test_symmetric_sweep_parity_and_reproducibility(n, dtype, oracle, gpu):
 	oracle.stage2(r_ref, v_ref, aa, T)
 	assert np.array_equal(rr, r_ref) and np.array_equal(vv, v_ref)
 	assert oracle.max_rel_err(outs[1][2], aa) <= (3e-7 if dtype == 'float32' else 1e-12) # run to run, per body
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_persistent_small_kernel_sizes_and_variants(dtype, oracle, gpu):
+	"""the automatic path up to ~9 400 bodies (csrc/nbody_small.cuh): edge sizes (one body, odd counts, one row
+	more or less than a warp / a CTA / the automatic range) and random sizes x every variant that fits.  All rows
+	against the float64 oracle, stage 2 bit-exact, steps(k) in ONE cooperative launch bit-identical to k single
+	steps, and bit-reproducible run to run (fixed summation order)"""
+	rng = np.random.default_rng(5)
+	names = gpu.small_variant_names()
+	cases = [(n, -1) for n in (1, 2, 3, 31, 32, 33, 63, 65, 255, 257, 4095, 4097, 9472)]
+	cases += [(int(rng.integers(2, 7000 if dtype == 'float64' else 14000)), gpu.SMALL_BASE + int(rng.integers(0, len(names)))) for _ in range(10)]
+	for case, (n, vid) in enumerate(cases):
+		r, v, m, G, T = oracle.uniform_universe(n, 300 + case, dtype)
+		v = (np.random.default_rng(case).standard_normal((n, 3)) * 1e-5).astype(dtype)
+		sh = gpu.Shard(n, dtype)
+		sh.upload(r, v, m, G, T)
+		if vid >= 0:
+			if not gpu.small_geometry(n, dtype, sh.info()['sm_count'], vid)['fits']:
+				with pytest.raises(gpu.GravB200Error, match = 'shared memory'):
+					sh.set_variant(vid)
+				sh.close()
+				continue
+			sh.set_variant(vid)
+		elif dtype == 'float64' and n > 7000:
+			sh.close() # 32 bytes per body: beyond one SM's shared memory, the symmetric sweep takes over
+			continue
+		assert sh.info()['variant'] >= gpu.SMALL_BASE, (n, vid)
+		sh.stage1(); sh.stage2()
+		r1, v1, a1 = sh.download(a = True)
+		if n > 1:
+			assert oracle.max_rel_err(a1, oracle.stage1_f64(r, m, G)) <= TOL_ACC[dtype], (n, vid)
+		r_ref, v_ref = r.copy(), v.copy()
+		oracle.stage2(r_ref, v_ref, a1, T)
+		assert np.array_equal(r1, r_ref) and np.array_equal(v1, v_ref), (n, vid)
+		launches0 = sh.info()['launches']
+		sh.steps(4)
+		assert sh.info()['launches'] - launches0 == 1
+		many = sh.download(a = True)
+		sh.upload(r1, v1, m, G, T)
+		for _ in range(4):
+			sh.stage1(); sh.stage2()
+		single = sh.download(a = True)
+		sh.close()
+		for x, y in zip(many, single):
+			assert np.array_equal(x, y), (n, vid)
 
 
 def test_symmetric_sweep_random_sizes_and_variants(oracle, gpu):
@@ -504,8 +563,8 @@ def test_symmetric_sweep_random_sizes_and_variants(oracle, gpu):
 
 
 def test_symmetric_sweep_on_two_gpus(oracle, gpu):
-	"""several shards: every shard sweeps its block rows symmetrically into a full-size accumulator, the
-	owner of a row adds all shards' partial sums over NVLink inside the integrate kernel"""
+	"""several shards: every shard sweeps its share of the universe's tile list symmetrically into a full-size
+	accumulator, the owner of a row adds all shards' partial sums over NVLink inside the integrate kernel"""
 	if gpu.device_count() < 2:
 		pytest.skip('needs 2 GPUs')
 	from gravitation_b200.kernel import b200
@@ -527,17 +586,17 @@ def test_symmetric_sweep_on_two_gpus(oracle, gpu):
 	assert traj_err(r3, r_ref) <= 5e-6
 
 
-@pytest.mark.parametrize('dtype,n', (('float32', 1 << 18), ('float64', (1 << 17) + 1000)))
-def test_symmetric_sweep_on_block_aligned_shards(dtype, n, oracle, gpu):
-	"""large universes on several GPUs: the shards are whole body-blocks of the one-GPU symmetric variant
-	(gravb200_partition rounds ceil(N/P) up when the predicted step time is shorter), so every GPU runs it; the last
-	shard is short.  Sampled rows against the oracle, then two more steps against a single GPU."""
+@pytest.mark.parametrize('dtype,n', (('float32', (1 << 18) + 77), ('float64', (1 << 17) + 1000)))
+def test_symmetric_sweep_on_uneven_shards(dtype, n, oracle, gpu):
+	"""large universes on several GPUs: rows are owned in plain ceil(N/P) slices (the last one short, nothing
+	aligned to body-blocks), while the symmetric sweep's flat tile list of the WHOLE universe is cut into equal
+	shares — block rows straddle shards.  Sampled rows against the oracle, then two more steps against a single GPU."""
 	if gpu.device_count() < 2:
 		pytest.skip('needs 2 GPUs')
 	from gravitation_b200.kernel import b200
 	parts = gpu.partition(n, 2, dtype)
 	iblk, variant = (3072, gpu.SYM_BASE) if dtype == 'float32' else (2048, gpu.SYM_BASE + 1) # the fastest variant of each dtype
-	assert parts[0][1] % iblk == 0 and parts[0][1] > parts[1][1] > 0 and parts[0][1] + parts[1][1] == n
+	assert parts == [(0, -(-n // 2)), (-(-n // 2), n // 2)] and parts[0][1] % iblk != 0
 	r, v, m, G, T = oracle.uniform_universe(n, 21, dtype)
 	u = b200.universe(T = T, G = G, scale_off = True, dtype = dtype, threads = 2)
 	u.add_objects(r, v, m, scale_off = True)
@@ -634,8 +693,8 @@ def test_upload_rows_and_download_rows_on_one_shard(dtype, oracle, gpu):
 @pytest.mark.parametrize('gpus', (2, 4, 8))
 @pytest.mark.parametrize('dtype,n', (('float32', 1 << 18), ('float64', (1 << 17) + 1000)))
 def test_symmetric_shards_agree_with_one_gpu(gpus, dtype, n, oracle, gpu):
-	"""2 / 4 / 8 shards with the symmetric sweep (block-aligned partition, peer reduction of the partial sums
-	over NVLink) against ONE GPU running the same universe, and sampled rows of every shard against the oracle.
+	"""2 / 4 / 8 shards with the symmetric sweep (equal shares of the universe's tile list, peer reduction of the
+	partial sums over NVLink inside the integrate kernel, hand-over flags instead of barrier launches) against ONE GPU running the same universe, and sampled rows of every shard against the oracle.
 	Self-skips on boxes with fewer GPUs."""
 	if gpu.device_count() < gpus:
 		pytest.skip('needs %d GPUs' % gpus)

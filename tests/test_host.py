@@ -323,20 +323,40 @@ def test_row_partition_covers_all_rows(shim):
 				if cnt:
 					assert row0 == pos
 				pos += cnt
-			# block alignment may cost imbalance only while the symmetric sweep still beats the ordered one
-			# (3.65 / 2.62 T inter/s fp32, 1.46 / 1.01 fp64), and never empties a shard once n >= world
-			assert max(c for _, c in parts) <= -(-n // world) * 1.39 + 1
-			assert n < world or min(c for _, c in parts) > 0
-			if world > 1 and n >= 32768:
-				iblks = (3072, 2048) if dtype == 'float32' else (1536, 2048)
-				assert any(parts[0][1] % b == 0 for b in iblks) or parts[0][1] == -(-n // world)
-	# the headline configuration: whole 3072-row blocks of the one-GPU symmetric variant on every full shard
-	parts = row_partition(1 << 20, 8, 'float32')
-	assert parts[0][1] == 43 * 3072 and all(r0 % 3072 == 0 for r0, _ in parts)
-	assert row_partition(1 << 18, 8, 'float64')[0][1] == 1 << 15 # already 16 blocks of 2048, the faster fp64 variant
-	assert row_partition((1 << 17) + 1000, 2, 'float64')[0][1] == 33 * 2048
-	assert row_partition(178225, 4, 'float32')[0][1] == 15 * 3072 # +3.4 % rows, but the symmetric sweep instead of the ordered one
-	assert row_partition(32768, 8, 'float32') == [(4096 * k, 4096) for k in range(8)] # 2 blocks of 3072 would empty the last shard
+			# ceil(n / world) rows per shard, the last one short (the symmetric sweep divides its WORK
+			# independently of the rows a shard owns, so nothing is rounded to body-blocks any more)
+			chunk = -(-n // world)
+			assert parts == [(min(k * chunk, n), max(0, min(chunk, n - k * chunk))) for k in range(world)]
+	assert row_partition(1 << 20, 8, 'float32') == [(131072 * k, 131072) for k in range(8)]
+	assert row_partition(178225, 4, 'float32')[3] == (3 * 44557, 178225 - 3 * 44557)
+
+
+def test_small_kernel_geometry(shim):
+	"""persistent small-N kernel (csrc/nbody_small.cuh): the host-side geometry covers every row and every
+	j-body exactly once, keeps at most 32 rows per row group, an even number of rows per CTA, whole unrolled
+	trips per slice, and fits the 227 KiB of shared memory wherever it says so"""
+	names = shim.small_variant_names()
+	assert len(names) >= 2 and all(nm.startswith('small_t') for nm in names)
+	for dtype, esz in (('float32', 4), ('float64', 8)):
+		for k, name in enumerate(names):
+			threads, unroll, rows = (int(name.split(key)[1].split('_')[0]) for key in ('_t', '_u', '_r'))
+			for sms in (148, 132, 8):
+				for n in (1, 2, 3, 16, 255, 256, 257, 1000, 4096, 4099, 6000, 8192, 9472, 9473, 14000, 16384):
+					try:
+						g = shim.small_geometry(n, dtype, sms, shim.SMALL_BASE + k)
+					except shim.GravB200Error:
+						assert -(-n // (32 * (threads // 32))) > sms # more rows per CTA than the variant has lanes for
+						continue
+					assert g['grid'] <= sms and g['grid'] * g['rows_per_cta'] >= n and (g['grid'] - 1) * g['rows_per_cta'] < n
+					assert g['rows_per_cta'] % 2 == 0 and g['rows_per_cta'] <= 32 * g['row_groups']
+					assert g['row_groups'] * g['slices'] == threads // 32
+					assert g['slice'] % (rows * unroll) == 0 and g['slices'] * g['slice'] >= n
+					assert g['smem_bytes'] >= 128 + g['slices'] * g['slice'] * 4 * esz
+					assert g['fits'] == (g['smem_bytes'] <= 227 * 1024)
+	# the automatic range on a B200: up to 64 rows per CTA on 148 SMs
+	assert shim.small_geometry(9472, 'float32')['row_groups'] == 2 and shim.small_geometry(9473, 'float32')['row_groups'] == 4
+	assert shim.small_geometry(4096, 'float32') == dict(grid = 128, rows_per_cta = 32, row_groups = 1, slice = 512, slices = 8,
+		smem_bytes = 128 + 4096 * 16 + 8 * 3 * 32 * 8, fits = True)
 
 
 # ---- worker protocol / analyze (cli/worker.py:115-245, cli/analyze.py:47-108) ----------------------
@@ -508,8 +528,8 @@ def test_symmetric_schedule_visits_every_block_pair_once(tmp_path):
 
 
 def test_row_partition_properties_hypothesis(shim):
-	"""random (n, world, dtype): slices are contiguous, cover [0, n), all but the last are equal, the last is
-	never empty for n >= world, and a non-plain shard size is a whole number of symmetric-sweep blocks"""
+	"""random (n, world, dtype): slices are contiguous, cover [0, n), hold ceil(n / world) rows each except the
+	short (possibly empty) tail"""
 	from hypothesis import given, settings, strategies as st
 
 	@settings(max_examples = 300, deadline = None)
@@ -523,13 +543,8 @@ def test_row_partition_properties_hypothesis(shim):
 		for row0, cnt in parts:
 			assert row0 == min(pos, n) and 0 <= cnt <= chunk
 			pos += chunk
-		plain = -(-n // world)
-		if chunk != plain:
-			assert n >= 32768 and world > 1 and chunk > plain
-			assert chunk % (3072 if dtype == 'float32' else 1536) == 0 or chunk % 2048 == 0
-			assert parts[-1][1] > 0 and chunk <= plain * 1.39 + 1
-		if n >= world:
-			assert all(cnt > 0 for _, cnt in parts) or chunk == plain
+		assert chunk == -(-n // world)
+		assert all(cnt == chunk for _, cnt in parts[:max(0, (n // chunk if chunk else 0))])
 	check()
 
 
@@ -539,7 +554,7 @@ def test_sass_of_the_default_kernels(shim):
 	"""cuobjdump -sass of libgravb200.so (sm_100a): the automatic large-N variants stage j-tiles with TMA bulk
 	copies (UBLKCP) behind mbarriers probed without blocking (SYNCS.PHASECHK, no TRYWAIT), compute with packed
 	FFMA2 / DFMA and MUFU.RSQ, keep everything in registers (no local-memory spills), and the symmetric
-	sweeps have no CTA-wide barrier after their prologue (one BAR for the mbarrier initialisation)"""
+	sweeps have no CTA-wide barrier inside their tile loop (BARs only around it: mbarrier initialisation, peer hand-over)"""
 	import collections, shutil, subprocess
 	tool = shutil.which('cuobjdump') or ('/usr/local/cuda/bin/cuobjdump' if os.path.isfile('/usr/local/cuda/bin/cuobjdump') else None)
 	if tool is None:
@@ -561,16 +576,22 @@ def test_sass_of_the_default_kernels(shim):
 		ins = funcs[names[0]]
 		return collections.Counter(i.split()[0].split('.')[0] for i in ins), ins
 	for key, must, bars in (
-		('sym_sweep_kernelILi256ELi12ELi512ELi3ELi2E', ('UBLKCP', 'FFMA2', 'FADD2', 'FMUL2', 'MUFU', 'SHFL', 'REDG', 'VOTE'), 1), # fp32 symmetric, variant 100
-		('sym_sweep_kernel_f64ILi256ELi8ELi256ELi3ELi1ELi1E', ('UBLKCP', 'DFMA', 'MUFU', 'SHFL', 'REDG', 'VOTE'), 1), # fp64 symmetric, variant 101
+		('sym_sweep_kernelILi256ELi12ELi512ELi3ELi2E', ('UBLKCP', 'FFMA2', 'FADD2', 'FMUL2', 'MUFU', 'SHFL', 'REDG', 'VOTE'), 4), # fp32 symmetric, variant 100
+		('sym_sweep_kernel_f64ILi256ELi8ELi256ELi3ELi1ELi1E', ('UBLKCP', 'DFMA', 'MUFU', 'SHFL', 'REDG', 'VOTE'), 4), # fp64 symmetric, variant 101
 		('sweep_kernelIfLi256ELi8ELi512ELi3ELi1ELi1ELi4ELi1E', ('UBLKCP', 'FFMA2', 'FADD2', 'FMUL2', 'MUFU', 'VOTE'), None), # fp32 ordered, variant 0
 		('sweep_kernelIdLi256ELi2ELi256ELi3ELi2ELi0ELi4ELi0E', ('UBLKCP', 'DFMA', 'MUFU', 'VOTE'), None), # fp64 ordered, variant 0
+		('small_steps_kernelIfLi256ELi4ELi4E', ('UBLKCP', 'FFMA2', 'FADD2', 'FMUL2', 'MUFU', 'VOTE', 'ATOMG', 'SHFL'), None), # fp32 persistent small-N, variant 200
+		('small_steps_kernelIdLi256ELi4ELi4E', ('UBLKCP', 'DFMA', 'MUFU', 'VOTE', 'ATOMG', 'SHFL'), None), # fp64 persistent small-N, variant 200
 		):
 		ops, ins = census(key)
 		for op in must:
-			assert ops[op] > 0, (key, op)
+			# fp64 accumulation into the global accumulator: RED, or ATOM without a result where a release fence follows
+			assert ops[op] > 0 or (op == 'REDG' and ops['ATOMG'] > 0), (key, op)
 		assert ops['STL'] == 0 and ops['LDL'] == 0, (key, 'spills to local memory')
 		assert any('PHASECHK' in i for i in ins) and not any('TRYWAIT' in i for i in ins), (key, 'mbarrier waits must be non-blocking probes')
 		assert any(i.startswith('MUFU.RSQ') for i in ins)
 		if bars is not None:
-			assert ops['BAR'] == bars, (key, ops['BAR'])
+			# mbarrier initialisation, the wait for the peers' flags at the start, the hand-over to the peers at the
+			# end (twice: idle CTAs leave early) — none of them inside the sweep loop
+			# (ncu: smsp__average_warps_issue_stalled_barrier = 0 in profiles/r0*_ncu_sym_*_summary.md)
+			assert 1 <= ops['BAR'] <= bars, (key, ops['BAR'])
