@@ -266,6 +266,7 @@ const std::vector<SmallVariant>& variants_small() {
     return v;
 }
 constexpr size_t kSmallMaxSmem = 227 * 1024;
+constexpr long long kSmallAutoMaxN = 12800;   // fp32, four row groups per CTA: 94 us at 12288, 106 at 13312 — the symmetric variant 101 takes ~99 us anywhere in 8192 .. 16384
 
 // Rows per shard (contiguous slices of ceil(n / world) rows, the last one short).  The rows
 // a shard OWNS (integrates, keeps velocities of) no longer shape the symmetric sweep: its flat (row, tile) list
@@ -464,7 +465,7 @@ int setup_small(gravb200_ctx* c, int sv, bool forced) {
     const int fit = small_geometry(c->n_total, c->dtype, c->sm_count, v, &g);
     if (fit == 1) return forced ? fail(GRAVB200_EINVAL, "variant %s: %lld bodies need more than %d rows per CTA", v.name, (long long)c->n_total, v.threads) : 1;
     if (fit == 2) return forced ? fail(GRAVB200_EINVAL, "variant %s: %lld bodies do not fit in shared memory (%zu bytes)", v.name, (long long)c->n_total, g.smem) : 1;
-    if (!forced && g.ng > (c->dtype == GRAVB200_F32 ? 2 : 1)) return 1;   // profiles/r02_small_n.jsonl: beyond, the large-N kernels win
+    if (!forced && !(c->dtype == GRAVB200_F32 ? (g.ng <= 2 || (g.ng == 4 && c->n_total <= kSmallAutoMaxN)) : g.ng == 1)) return 1;   // profiles/r02_small_n.jsonl: beyond, the large-N kernels win
     const void* fn = v.fn[c->dtype == GRAVB200_F32 ? 0 : 1];
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     int occ = 0;
@@ -549,7 +550,7 @@ int pick_variant(gravb200_ctx* c) {
         int sv = -1;
         if (c->forced_variant >= kSymBase) sv = c->forced_variant - kSymBase;
         else if (c->forced_variant < 0 && c->n_total >= c->sym_min_n)
-            sv = c->dtype == GRAVB200_F32 ? (c->n_total >= 65536 ? 0 : (c->n_total >= 16384 ? 1 : 6))
+            sv = c->dtype == GRAVB200_F32 ? (c->n_total >= 65536 ? 0 : (c->n_total > kSmallAutoMaxN ? 1 : 6))
                                           : (c->n_total >= 16384 ? 1 : 2);   // profiles/r01_sym*_variants_sweep*.txt
         if (sv >= 0) return setup_sym(c, sv);
     } else if (c->world > 1 && c->peer_mode && c->acc64) {

@@ -29,6 +29,19 @@
 
 #include <type_traits>
 
+// A/B switches of the ordered fp32 sweep (scripts/dbg/ab.py builds).  Scalar loads of the i-bodies take every register
+// move out of its j-loop (569 -> 487 instructions per unrolled trip of variant 0, see ld_cg_f32) and negating the
+// i-positions once per i-block takes out 24 FADD more (-> 469) — and the kernel gets SLOWER: 2.625 -> 2.589 /
+// 2.607 / 2.575 T interactions/s at N = 2^20 (profiles/r02_ordered_ab.jsonl).  It is bound by the operand fetch of
+// the packed FFMA2, not by issue slots; the copies ptxas makes happen to sit in friendlier
+// register banks.  Both stay off; the persistent small-N kernel (two warps per scheduler, issue bound) needs them.
+#ifndef ORDERED_SCALAR_LOADS
+#define ORDERED_SCALAR_LOADS 0
+#endif
+#ifndef ORDERED_NEG_ONCE
+#define ORDERED_NEG_ONCE 0
+#endif
+
 namespace gravb200 {
 
 constexpr int kMaxPeers = 15;   // one 16-GPU NVSwitch domain at most
@@ -131,6 +144,16 @@ __device__ __forceinline__ double mass_over_r3(double m, double d2) {
 __device__ __forceinline__ double ld_cg_f64(const double* p) {
     double v;
     asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+// One scalar, never merged into a vector load (asm): coordinates that feed packed f32x2 instructions as the pair
+// (x of body 2c, x of body 2c + 1) must sit in an aligned register pair.  Components that arrive as one 128-bit
+// load result stay in that register quad and ptxas re-assembles every pair with two MOVs before EVERY use
+// (2.6 - 4.75 extra instructions per pair of interactions in the ordered sweeps, profiles/r02_small_n.md).
+__device__ __forceinline__ float ld_cg_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
 
@@ -427,8 +450,16 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
                 const long long il = (long long)ib * IBLK + r * THREADS + tid;
                 V4 b;
                 b.x = 0; b.y = 0; b.z = 0; b.w = 0;
-                if (il < p.n_local) b = posf[p.row0 + il];
-                xi[r] = b.x; yi[r] = b.y; zi[r] = b.z;
+                if constexpr (F32 && PACK && ORDERED_SCALAR_LOADS) {
+                    if (il < p.n_local) {   // scalar loads: see ld_cg_f32
+                        const float* src = reinterpret_cast<const float*>(posf + p.row0 + il);
+                        b.x = ld_cg_f32(src); b.y = ld_cg_f32(src + 1); b.z = ld_cg_f32(src + 2);
+                    }
+                } else {
+                    if (il < p.n_local) b = posf[p.row0 + il];
+                }
+                if constexpr (F32 && PACK && ORDERED_NEG_ONCE) { xi[r] = -b.x; yi[r] = -b.y; zi[r] = -b.z; }   // packed path: d = r_j + (-r_i), negated once per i-block
+                else { xi[r] = b.x; yi[r] = b.y; zi[r] = b.z; }
                 if constexpr (SS) {
                     ssum[(0 * R + r) * THREADS + tid] = 0.0;
                     ssum[(1 * R + r) * THREADS + tid] = 0.0;
@@ -475,9 +506,10 @@ __global__ void __launch_bounds__(THREADS, MINB) sweep_kernel(const SweepParams 
                 auto interact = [&](const float4 b, auto masked, const int dj) {
 #pragma unroll
                     for (int q = 0; q < P; ++q) {
-                        const float2 dx = __fadd2_rn(make_float2(b.x, b.x), make_float2(-xi[2 * q], -xi[2 * q + 1]));
-                        const float2 dy = __fadd2_rn(make_float2(b.y, b.y), make_float2(-yi[2 * q], -yi[2 * q + 1]));
-                        const float2 dz = __fadd2_rn(make_float2(b.z, b.z), make_float2(-zi[2 * q], -zi[2 * q + 1]));
+                        constexpr float sg = ORDERED_NEG_ONCE ? 1.f : -1.f;   // folds away
+                        const float2 dx = __fadd2_rn(make_float2(b.x, b.x), make_float2(sg * xi[2 * q], sg * xi[2 * q + 1]));
+                        const float2 dy = __fadd2_rn(make_float2(b.y, b.y), make_float2(sg * yi[2 * q], sg * yi[2 * q + 1]));
+                        const float2 dz = __fadd2_rn(make_float2(b.z, b.z), make_float2(sg * zi[2 * q], sg * zi[2 * q + 1]));
                         float2 d2 = __ffma2_rn(dx, dx, make_float2(e2, e2));
                         d2 = __ffma2_rn(dy, dy, d2);
                         d2 = __ffma2_rn(dz, dz, d2);

@@ -64,6 +64,19 @@ template <typename REAL> __device__ __forceinline__ REAL small_far();
 template <> __device__ __forceinline__ float small_far<float>() { return 1.0e30f; }
 template <> __device__ __forceinline__ double small_far<double>() { return 1.0e150; }
 
+#ifdef SMALL_DEBUG   // dev builds: time stamps (ns) of the middle CTA's last step, scripts/dbg/small_dbg.py
+#define SMALL_STAMP(i)                                                                         \
+    do {                                                                                       \
+        if (p.clk && blockIdx.x == gridDim.x / 2 && step == p.k - 1) {                         \
+            unsigned long long t_;                                                             \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                             \
+            p.clk[64 + (i)] = t_;                                                              \
+        }                                                                                      \
+    } while (0)
+#else
+#define SMALL_STAMP(i) do {} while (0)
+#endif
+
 template <typename REAL>
 constexpr size_t small_smem_bytes(int n_slots, int nsl, int ng) {
     return 128 + (size_t)n_slots * 4 * sizeof(REAL) + (size_t)nsl * 3 * 32 * ng * sizeof(double);
@@ -137,6 +150,7 @@ __global__ void __launch_bounds__(THREADS, 1) small_steps_kernel(const SmallPara
     int front = p.front;
     for (int step = 0; step < p.k; ++step) {
         const V4* __restrict__ posf = reinterpret_cast<const V4*>(p.pos[front]);
+        if (tid == 0) SMALL_STAMP(0);
         if (warp == 0) {
             if (step > 0) {
                 // grid barrier: every CTA has stored its r' of step - 1 (arrival below, after the stores)
@@ -152,20 +166,20 @@ __global__ void __launch_bounds__(THREADS, 1) small_steps_kernel(const SmallPara
                     }
                 } while (!__all_sync(0xffffffffu, ok ? 1 : 0));
             }
-            if (lane == 0) {
+            if (lane == 0) SMALL_STAMP(1);
+            if (lane < nsl) {   // lane s issues the copy of slice s (one lane looping over the slices took 0.9 us at 8 slices)
                 fence_proxy_async_all();   // r' came from ordinary stores; the bulk copies below read it through the async proxy
-                for (int s = 0; s < nsl; ++s) {
-                    const int j0 = s * p.slice;
-                    const int cnt = min(p.slice, n - j0);
-                    if (cnt > 0) {
-                        const uint32_t bytes = (uint32_t)((size_t)cnt * sizeof(V4));
-                        mbar_expect_tx(&full[s], bytes);
-                        tma_bulk_g2s(tile + j0, posf + j0, bytes, &full[s]);
-                    } else {
-                        mbar_arrive(&full[s]);   // nothing to copy: complete the phase
-                    }
+                const int j0 = lane * p.slice;
+                const int cnt = min(p.slice, n - j0);
+                if (cnt > 0) {
+                    const uint32_t bytes = (uint32_t)((size_t)cnt * sizeof(V4));
+                    mbar_expect_tx(&full[lane], bytes);
+                    tma_bulk_g2s(tile + j0, posf + j0, bytes, &full[lane]);
+                } else {
+                    mbar_arrive(&full[lane]);   // nothing to copy: complete the phase
                 }
             }
+            if (lane == 0) SMALL_STAMP(2);
             __syncwarp();
         }
 
@@ -174,12 +188,32 @@ __global__ void __launch_bounds__(THREADS, 1) small_steps_kernel(const SmallPara
         REAL nx[R], ny[R], nz[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            V4 b;
-            b.x = b.y = b.z = small_far<REAL>(); b.w = 0;
-            if (rl0 + r < p.rpc && i0 + r < n) b = ld_cg_v4(posf + i0 + r);
-            nx[r] = -b.x; ny[r] = -b.y; nz[r] = -b.z;
+            nx[r] = ny[r] = nz[r] = -small_far<REAL>();
+            if (rl0 + r < p.rpc && i0 + r < n) {
+                if constexpr (F32) {
+                    // three SCALAR loads on purpose: the pair (x of row 2c, x of row 2c + 1) feeds packed instructions
+                    // and must sit in an aligned register pair; components that arrive as one 128-bit load result
+                    // stay in that quad and ptxas re-assembles the pair with two MOVs before every use (4.75 extra
+                    // instructions per pair of interactions)
+                    const float* src = reinterpret_cast<const float*>(posf + i0 + r);
+                    nx[r] = -ld_cg_f32(src); ny[r] = -ld_cg_f32(src + 1); nz[r] = -ld_cg_f32(src + 2);
+                } else {
+                    const V4 b = ld_cg_v4(posf + i0 + r);
+                    nx[r] = -b.x; ny[r] = -b.y; nz[r] = -b.z;
+                }
+            }
+        }
+        float2 px[P], py[P], pz[P];
+        if constexpr (F32) {
+#pragma unroll
+            for (int c = 0; c < P; ++c) {
+                px[c] = make_float2(nx[2 * c], nx[2 * c + 1]);
+                py[c] = make_float2(ny[2 * c], ny[2 * c + 1]);
+                pz[c] = make_float2(nz[2 * c], nz[2 * c + 1]);
+            }
         }
         mbar_wait_warp(&full[sl], (uint32_t)(step & 1));
+        if (lane == 0) SMALL_STAMP(3 + warp);
         const V4* __restrict__ tj = tile + sl0 + q;
         const int dj0 = sl0 + q - i0;   // j - i0 at t = 0
 
@@ -194,9 +228,9 @@ __global__ void __launch_bounds__(THREADS, 1) small_steps_kernel(const SmallPara
             auto interact = [&](const float4 b, auto masked, const int dj) {
 #pragma unroll
                 for (int c = 0; c < P; ++c) {
-                    const float2 dx = __fadd2_rn(make_float2(b.x, b.x), make_float2(nx[2 * c], nx[2 * c + 1]));
-                    const float2 dy = __fadd2_rn(make_float2(b.y, b.y), make_float2(ny[2 * c], ny[2 * c + 1]));
-                    const float2 dz = __fadd2_rn(make_float2(b.z, b.z), make_float2(nz[2 * c], nz[2 * c + 1]));
+                    const float2 dx = __fadd2_rn(make_float2(b.x, b.x), px[c]);
+                    const float2 dy = __fadd2_rn(make_float2(b.y, b.y), py[c]);
+                    const float2 dz = __fadd2_rn(make_float2(b.z, b.z), pz[c]);
                     float2 d2 = __ffma2_rn(dx, dx, make_float2(e2, e2));
                     d2 = __ffma2_rn(dy, dy, d2);
                     d2 = __ffma2_rn(dz, dz, d2);
@@ -256,6 +290,7 @@ __global__ void __launch_bounds__(THREADS, 1) small_steps_kernel(const SmallPara
             run(tb, t_real, std::false_type{});
         }
 
+        if (lane == 0) SMALL_STAMP(19 + warp);
         // the R j-sub-slices of the warp (fixed butterfly order), then the slices in order through shared memory
 #pragma unroll
         for (int off = LPS; off < 32; off <<= 1) {
@@ -272,6 +307,7 @@ __global__ void __launch_bounds__(THREADS, 1) small_steps_kernel(const SmallPara
             for (int r = 0; r < R; ++r) { rs[r] = sx[r]; rs[rows_cta + r] = sy[r]; rs[2 * rows_cta + r] = sz[r]; }
         }
         __syncthreads();
+        if (tid == 0) SMALL_STAMP(35);
         if (owner) {
             double tx = 0.0, ty = 0.0, tz = 0.0;
             for (int s = 0; s < nsl; ++s) {
@@ -312,6 +348,7 @@ __global__ void __launch_bounds__(THREADS, 1) small_steps_kernel(const SmallPara
         }
         // everybody is done with `tile` and `red` of this step; the CTA's r' is stored: arrive at the grid barrier
         __syncthreads();
+        if (tid == 0) SMALL_STAMP(36);
         if (step + 1 < p.k && tid == 0) {
             __threadfence();
             atomicAdd(p.gbar, 1ull);

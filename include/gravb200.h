@@ -133,7 +133,7 @@ int gravb200_info(const gravb200_ctx* ctx, int64_t* info, int n);
  * the ordered sweeps (bit-reproducible), ids 100 + k, k < gravb200_sym_variant_count(dtype), the symmetric sweeps
  * (every unordered pair once, fp64 atomics: reproducible up to fp64 rounding of the cross-tile sum), ids 200 + k,
  * k < gravb200_small_variant_count(), the persistent multi-step kernel for universes that fit one SM's shared
- * memory (one shard, bit-reproducible; the automatic choice up to 64 rows per SM, ~9 400 bodies on a B200 —
+ * memory (one shard, bit-reproducible; the automatic choice up to 12 800 bodies in float32, 4 736 in float64 —
  * there gravb200_steps(k) is ONE cooperative launch with a grid barrier between the steps). */
 int gravb200_set_variant(gravb200_ctx* ctx, int variant);
 int gravb200_variant_count(int dtype);

@@ -14,7 +14,7 @@ K = 256
 for dtype in ('float32', 'float64'):
     small = list(range(_shim.SMALL_BASE, _shim.SMALL_BASE + len(_shim.small_variant_names())))
     old = {'float32': [3, 2, 106, 101], 'float64': [2, 1, 102, 101]}[dtype]
-    sizes = [16, 64, 256, 1024, 2048, 3000, 4096, 6000, 8192, 9472, 12288, 16384]
+    sizes = [16, 64, 256, 1024, 2048, 3000, 4096, 6000, 8192, 9472, 12288, 13312, 14000, 16384]
     if quick:
         sizes = [256, 4096, 8192]
     for n in sizes:

@@ -189,7 +189,7 @@ def test_steps_equals_repeated_stage_calls_and_is_deterministic(dtype, oracle, g
 
 
 @pytest.mark.parametrize('dtype', DTYPES)
-@pytest.mark.parametrize('n,variant', ((700, -1), (700, 3), (2048 + 77, 1), (9000, -1), (9000, 102), (12000, -1)))
+@pytest.mark.parametrize('n,variant', ((700, -1), (700, 3), (2048 + 77, 1), (9000, -1), (9000, 102), (12000, -1), (14000, -1)))
 def test_graph_replayed_steps_equal_single_steps(n, variant, dtype, oracle, gpu):
 	"""steps(k) is ONE cooperative launch of the persistent kernel for small universes (automatic choice up to
 	~9 400 bodies) and replays groups of 8 steps from a CUDA graph on the other launch-bound sizes (plus single
@@ -217,7 +217,7 @@ def test_graph_replayed_steps_equal_single_steps(n, variant, dtype, oracle, gpu)
 				sh.steps(k)
 			vid = sh.info()['variant']
 			symmetric = gpu.SYM_BASE <= vid < gpu.SMALL_BASE
-			small_range = n <= 9472 and gpu.small_geometry(n, dtype, sh.info()['sm_count'])['fits'] # fp64: 32 bytes per body
+			small_range = n <= (12800 if dtype == 'float32' else 4736) # the automatic range of the persistent kernel on 148 SMs
 			if vid >= gpu.SMALL_BASE:
 				assert variant < 0 and small_range
 				assert sh.info()['launches'] - launches0 == (k if mode == 'stages' else 1)
@@ -461,9 +461,9 @@ def test_accuracy_command_float32_against_float64(gpu):
 
 
 @pytest.mark.parametrize('dtype', DTYPES)
-@pytest.mark.parametrize('n', (9473, 10007, 40000))
+@pytest.mark.parametrize('n', (12801, 20011, 40000))
 def test_symmetric_sweep_parity_and_reproducibility(n, dtype, oracle, gpu):
-	"""the default path above the persistent small-N kernel's range (N > 9472 on 148 SMs): every unordered pair once (nbody_sym.cuh).  Parity against
+	"""the default path above the persistent small-N kernel's range (N > 12800 fp32): every unordered pair once (nbody_sym.cuh).  Parity against
 	the float64 oracle, bit-exact stage 2, and run-to-run agreement (fp64 atomics: reproducible up to the
 	rounding of the cross-tile fp64 sum, far below float32 resolution)"""
 	r, v, m, G, T = oracle.uniform_universe(n, 77, dtype)
@@ -493,7 +493,7 @@ def test_persistent_small_kernel_sizes_and_variants(dtype, oracle, gpu):
 	steps, and bit-reproducible run to run (fixed summation order)"""
 	rng = np.random.default_rng(5)
 	names = gpu.small_variant_names()
-	cases = [(n, -1) for n in (1, 2, 3, 31, 32, 33, 63, 65, 255, 257, 4095, 4097, 9472)]
+	cases = [(n, -1) for n in (1, 2, 3, 31, 32, 33, 63, 65, 255, 257, 4095, 4097, 4736, 9472, 12800)]
 	cases += [(int(rng.integers(2, 7000 if dtype == 'float64' else 14000)), gpu.SMALL_BASE + int(rng.integers(0, len(names)))) for _ in range(10)]
 	for case, (n, vid) in enumerate(cases):
 		r, v, m, G, T = oracle.uniform_universe(n, 300 + case, dtype)
@@ -507,8 +507,9 @@ def test_persistent_small_kernel_sizes_and_variants(dtype, oracle, gpu):
 				sh.close()
 				continue
 			sh.set_variant(vid)
-		elif dtype == 'float64' and n > 7000:
-			sh.close() # 32 bytes per body: beyond one SM's shared memory, the symmetric sweep takes over
+		elif dtype == 'float64' and n > 4736:
+			assert sh.info()['variant'] < gpu.SMALL_BASE # fp64: the automatic range ends at 32 rows per CTA
+			sh.close()
 			continue
 		assert sh.info()['variant'] >= gpu.SMALL_BASE, (n, vid)
 		sh.stage1(); sh.stage2()
