@@ -240,6 +240,7 @@ def device_leg(env, n, dtype, steps, warmup, parity_rows):
 	def one_step():
 		env.flush_l2()
 		env.barrier()
+		shard.peer_barrier() # several GPUs: the timed events start when every rank's stream has got here (no host launch skew in the step)
 		shard.stage1()
 		shard.stage2()
 		t = shard.timings()
@@ -452,7 +453,13 @@ def own_arm(args):
 
 	exchange = None
 	if world > 1:
-		exchange = 'fused peer-store exchange over NVLink (CUDA IPC) + flag barrier' if info['exchange_mode'] == 1 else 'NCCL all-gather of positions'
+		if info['exchange_mode'] != 1:
+			exchange = 'NCCL all-gather of positions'
+		elif symmetric:
+			exchange = ('stream-K shares of the universe\'s tile list per GPU; reduce-scatter of the partial sums + peer stores of r\' inside the '
+				'integrate kernel over NVLink (CUDA IPC), hand-over flags folded into the sweep / integrate kernels (no barrier launches)')
+		else:
+			exchange = 'fused peer-store exchange over NVLink (CUDA IPC) in the sweep epilogue + flag barrier'
 	line = {
 		'metric': METRIC if (args.bodies == 20 and dtype == 'float32') else 'G body-interactions/s at N=2^%d %s' % (args.bodies, args.dtype),
 		'value': main['value'], 'unit': UNIT,
@@ -467,6 +474,7 @@ def own_arm(args):
 			'grid': info['grid'], 'threads': info['threads'], 'bodies_per_thread': info['bodies_per_thread'], 'tile': info['tile'],
 			'variant': info['variant'],
 			'l2': 'flushed between timed steps (256 MiB write); the position array is then re-read from L2 by design',
+			'start': 'every timed step starts behind a device-side flag barrier of all ranks (host launch skew is not part of the step)' if world > 1 else 'single stream',
 			},
 		'per_gpu': {'g_inter_s': per_gpu_rate, 'rows_rank0': int(main['rows']), 'rows_even_share': -(-n // world),
 			'sweep_ms': float(np.mean(main['sweep_ms'])), 'exchange_ms': float(np.mean(main['xchg_ms'])),

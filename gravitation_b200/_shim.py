@@ -44,6 +44,7 @@ _SIGNATURES = [
 	('gravb200_stage1', ctypes.c_int, [_c_ctx]),
 	('gravb200_stage2', ctypes.c_int, [_c_ctx]),
 	('gravb200_exchange', ctypes.c_int, [_c_ctx]),
+	('gravb200_peer_barrier', ctypes.c_int, [_c_ctx]),
 	('gravb200_group_begin', ctypes.c_int, []),
 	('gravb200_group_end', ctypes.c_int, []),
 	('gravb200_peer_export', ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
@@ -351,6 +352,10 @@ class Shard:
 		_check(self._lib.gravb200_info(self._ctx, v, 12))
 		keys = ('grid', 'threads', 'bodies_per_thread', 'tile', 'stages', 'smem_bytes', 'launches', 'sm_count', 'packed', 'ctas_per_sm', 'exchange_mode', 'variant')
 		return dict(zip(keys, [int(x) for x in v]))
+
+	def peer_barrier(self):
+		"""enqueue a flag barrier with all peer shards (collective; no-op on one shard / in NCCL mode)"""
+		_check(self._lib.gravb200_peer_barrier(self._ctx))
 
 	def set_variant(self, variant):
 		_check(self._lib.gravb200_set_variant(self._ctx, int(variant)))

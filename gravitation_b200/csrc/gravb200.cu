@@ -1298,6 +1298,14 @@ int gravb200_exchange(gravb200_ctx* c) {
     return 0;
 }
 
+int gravb200_peer_barrier(gravb200_ctx* c) {
+    if (!c) return fail(GRAVB200_EINVAL, "ctx is NULL");
+    if (c->world == 1 || !c->peer_mode) return 0;
+    if (c->pending) return fail(GRAVB200_EINVAL, "peer barrier between stage1 and stage2");
+    CU(cudaSetDevice(c->device));
+    return peer_barrier(c);
+}
+
 int gravb200_group_begin(void) {
     int rc = nccl_load();
     if (rc) return rc;

@@ -82,6 +82,12 @@ int gravb200_stage1(gravb200_ctx* ctx);
 /* Replaces: step_stage2() (np2.py:110-115 / pc2.py:164-168).  Commits the back buffers (multi-GPU:
  * after the all-gather of new positions) and blocks until the device is idle. */
 int gravb200_stage2(gravb200_ctx* ctx);
+/* Enqueue a flag barrier with all peer shards on the context's stream (peer-store mode; a no-op on one shard and in
+ * NCCL mode).  Collective: every shard calls it, between steps.  What follows on the stream starts when every shard
+ * has got here — bench.py aligns the shards with it before a timed step, so host launch skew between the ranks'
+ * processes is not charged to the step. */
+int gravb200_peer_barrier(gravb200_ctx* ctx);
+
 /* Multi-GPU only: enqueue the all-gather of the new positions of the pending step without waiting
  * (gravb200_stage2 does it itself if it was not called).  A host thread that drives SEVERAL contexts must
  * bracket their gravb200_exchange calls with gravb200_group_begin/end (ncclGroupStart/End semantics). */
