@@ -309,6 +309,9 @@ __global__ void unpack_kernel(const V4* __restrict__ in, REAL* out3, long long n
 
 }  // namespace
 
+// layout of a context's peer-visible flag array (u64 words): barrier generations | sweep done | integrate done | sweep stats (items, ns)
+constexpr int kFlagsSweep = kMaxPeers + 1, kFlagsIntegrate = 2 * (kMaxPeers + 1), kFlagsBalance = 3 * (kMaxPeers + 1), kFlagsTotal = 5 * (kMaxPeers + 1);
+
 struct gravb200_ctx {
     int dtype = 0, device = 0, rank = 0, world = 1;
     size_t esz = 4;            // sizeof(REAL)
@@ -350,6 +353,8 @@ struct gravb200_ctx {
     // ([kFlagsSweep + q]: shard q's sweep of step e is done, [kFlagsIntegrate + q]: its integrate), one arrival
     // counter per kernel, and the step generation (lockstep on all ranks)
     unsigned int* done_ctr = nullptr;             // [2]
+    unsigned long long* tstart = nullptr;         // earliest CTA start of the running sweep (speed-proportional shares)
+    bool sym_balance = false;                     // shares of the flat list follow the measured sweep speed of every GPU
     unsigned long long sym_epoch = 0;
     bool sym_tail_pending = false;                // the last enqueued step has not been followed by its tail wait
     // symmetric sweep (fp32): global fp64 accumulator and the flat-item offsets of the local block rows
@@ -437,6 +442,12 @@ int setup_sym(gravb200_ctx* c, int sv) {
     c->sym_hi = sk_lo(rs[nib], c->rank + 1, c->world);
     c->occ = occ;
     c->grid = (int)std::max<long long>(1, std::min<long long>((long long)occ * c->sm_count, c->sym_hi - c->sym_lo));
+    // several shards with long sweeps (>= 16 tiles per CTA): the shares follow the measured speed of each GPU
+    // (nbody_sym.cuh, SymBalance); GRAVB200_BALANCE=0 keeps the equal shares
+    const char* bal_env = getenv("GRAVB200_BALANCE");
+    c->sym_balance = c->world > 1 && (c->sym_hi - c->sym_lo) >= 16LL * c->grid && !(bal_env && bal_env[0] == '0');
+    if (c->world > 1)   // a new variant counts tiles of another size: forget the published speeds
+        CU(cudaMemsetAsync(c->flags + kFlagsBalance, 0, 2 * (kMaxPeers + 1) * sizeof(unsigned long long), c->stream));
     c->use_sym = true;
     return 0;
 }
@@ -517,7 +528,6 @@ int launch_small(gravb200_ctx* c, int k, int integrate) {
 // CUDA graph of kGraphSteps (even: the front buffer is the same before and after) full steps.  Kernel
 // arguments depend only on the front-buffer parity, the variant and G/T/eps, so a graph stays valid until
 // one of those changes (pick_variant, upload).
-constexpr int kFlagsSweep = kMaxPeers + 1, kFlagsIntegrate = 2 * (kMaxPeers + 1), kFlagsTotal = 3 * (kMaxPeers + 1);
 constexpr int kGraphSteps = 8;
 constexpr int64_t kGraphMaxN = 32768;   // above, a step takes > 0.3 ms and launch latency is noise
 
@@ -689,6 +699,11 @@ int launch_sweep(gravb200_ctx* c, int integrate) {
                 b.signal_flags[q] = c->peer_flags[q] + kFlagsIntegrate;
                 ip.acc_src[ip.n_src++] = c->peer_acc[q];
                 if (q != c->rank) ip.sp.peer_back[ip.sp.n_peers++] = c->peer_pos[c->front ^ 1][q];
+            }
+            if (c->sym_balance) {
+                sp.bal.stats = c->flags + kFlagsBalance;
+                sp.bal.tstart = c->tstart;
+                for (int q = 0; q < c->world; ++q) sp.bal.peer_stats[q] = c->peer_flags[q] + kFlagsBalance;
             }
         }
         void* sargs[] = {&sp};
@@ -1149,6 +1164,8 @@ int gravb200_ctx_create(int64_t n_total, int dtype, int device, int rank, int wo
     CUX(cudaMemsetAsync(c->flags, 0, kFlagsTotal * sizeof(unsigned long long), c->stream));
     CUX(cudaMalloc(&c->done_ctr, 2 * sizeof(unsigned int)));
     CUX(cudaMemsetAsync(c->done_ctr, 0, 2 * sizeof(unsigned int), c->stream));
+    CUX(cudaMalloc(&c->tstart, sizeof(unsigned long long)));
+    CUX(cudaMemsetAsync(c->tstart, 0xff, sizeof(unsigned long long), c->stream));
     if (world > 1) {   // symmetric sweep accumulator: must exist before peer_export
         CUX(cudaMalloc(&c->acc64, (size_t)c->n_pad * 4 * sizeof(double)));
         CUX(cudaMemsetAsync(c->acc64, 0, (size_t)c->n_pad * 4 * sizeof(double), c->stream));
@@ -1199,6 +1216,7 @@ int gravb200_ctx_destroy(gravb200_ctx* c) {
     }
     if (c->flags) cudaFree(c->flags);
     if (c->done_ctr) cudaFree(c->done_ctr);
+    if (c->tstart) cudaFree(c->tstart);
     if (c->acc64) cudaFree(c->acc64);
     if (c->row_start) cudaFree(c->row_start);
     if (c->xerr) cudaFree(c->xerr);
@@ -1423,6 +1441,11 @@ int gravb200_timings(gravb200_ctx* c, float* ms, int n) {
         if (n > 4) ms[4] = (float)((double)h[1] * 1e-6);   // lifetime of CTA 0 of the last sweep, ms
         if (n > 7 && c->tev_ok && c->use_sym && c->world > 1 && cudaEventQuery(c->tev[3]) == cudaSuccess)
             for (int i = 0; i < 3; ++i) CU(cudaEventElapsedTime(&ms[5 + i], c->tev[i], c->tev[i + 1]));
+        if (n > 8 && c->use_sym && c->world > 1 && c->sym_balance) {   // this shard's share of the last sweep against the equal share
+            unsigned long long items = 0;
+            CU(cudaMemcpy(&items, c->flags + kFlagsBalance + c->rank, sizeof(items), cudaMemcpyDeviceToHost));
+            if (items && c->sym_total > 0) ms[8] = (float)((double)items * c->world / (double)c->sym_total);
+        }
 #ifdef SYM_DEBUG
         if (n > 16) {   // [2036..2046] divergence counters of SYM_DIVCHK, [2047] cycles spent in jbar waits
             unsigned long long d[12];

@@ -44,6 +44,17 @@ namespace gravb200 {
 #define SYM_DIVCHK(i) do {} while (0)
 #endif
 
+// Several shards: the shares of the flat list follow the MEASURED speed of each GPU.  Every shard's last sweep
+// publishes (items, nanoseconds) to all shards; the next sweep cuts the list in proportion to items / ns — computed
+// on the device by every CTA's first thread from the same numbers with the same arithmetic, so all shards agree
+// on the boundaries without a host round trip.  The GPUs of one box differ by ~0.5 % under this load, and a step
+// takes as long as its slowest sweep (profiles/r02_bench_n8*.json: rank 0's sweep 37.77 / 37.94 ms on two boxes).
+struct SymBalance {
+    const unsigned long long* stats;                  // local [2][kMaxPeers + 1]: items, ns of every shard's previous sweep; nullptr: equal shares
+    unsigned long long* peer_stats[kMaxPeers + 1];    // that array on every shard (entries [rank] are ours to write)
+    unsigned long long* tstart;                       // local: earliest CTA start of this launch
+};
+
 struct SymParams {
     const float4* pos_front;      // [n_pad] {x,y,z,m} of all bodies (fp32 kernel)
     const double4* pos_front_d;   // same, fp64 kernel
@@ -61,7 +72,75 @@ struct SymParams {
     // equal range per shard — stream-K across GPUs, whatever the row ownership of the integrate step is.
     long long item_lo, item_hi;
     PeerSync sync;                // several shards: hand-over with the peers' integrate kernels (nbody_kernels.cuh)
+    SymBalance bal;               // several shards, long sweeps: speed-proportional shares instead of [item_lo, item_hi)
 };
+
+// this launch's share of the flat list; all threads call it (CTA barrier inside when balancing)
+__device__ __forceinline__ void sym_share(const SymParams& p, long long& share_lo, long long& share_hi) {
+    share_lo = p.item_lo; share_hi = p.item_hi;
+    if (p.bal.stats == nullptr) return;
+    __shared__ long long s_share[2];
+    if (threadIdx.x == 0) {
+        const int P = p.sync.world, me = p.sync.rank;
+        const long long total = p.row_start[p.n_iblocks];
+        // weight of shard q = items / ns of its previous sweep; two passes instead of an array (no local memory)
+        auto weight = [&](int q) -> double {
+            const unsigned long long items = p.bal.stats[q], ns = p.bal.stats[(kMaxPeers + 1) + q];
+            return (items == 0 || ns == 0) ? 0.0 : (double)items / (double)ns;
+        };
+        double sum = 0.0, c0 = 0.0;
+        bool ok = true;
+        for (int q = 0; q < P; ++q) {   // the same additions in the same order on every shard
+            const double wq = weight(q);
+            if (wq == 0.0) ok = false;
+            if (q == me) c0 = sum;
+            sum += wq;
+        }
+        long long lo = p.item_lo, hi = p.item_hi;
+        if (ok) {
+            const double c1 = c0 + weight(me);
+            lo = me == 0 ? 0 : (long long)((double)total * (c0 / sum));
+            hi = me == P - 1 ? total : (long long)((double)total * (c1 / sum));
+            if (lo > total) lo = total;
+            if (hi > total) hi = total;
+            if (hi < lo) hi = lo;
+        }
+        s_share[0] = lo; s_share[1] = hi;
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        atomicMin(p.bal.tstart, now);
+    }
+    __syncthreads();
+    share_lo = s_share[0]; share_hi = s_share[1];
+}
+
+// end of a sweep CTA: peer_signal plus, from the last CTA, this sweep's (items, ns) for everybody's next shares
+__device__ __forceinline__ void sym_finish(const SymParams& p, long long share_items) {
+    const PeerSync& s = p.sync;
+    if (s.done_ctr == nullptr) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned int old = atomicAdd(s.done_ctr, 1u);
+        if (old == gridDim.x - 1) {
+            *s.done_ctr = 0;
+            if (p.bal.stats) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                const unsigned long long t0 = atomicExch(p.bal.tstart, ~0ull);   // earliest start of this launch; reset for the next
+                const unsigned long long ns = now > t0 ? now - t0 : 0ull;
+                for (int q = 0; q < s.world; ++q) {
+                    p.bal.peer_stats[q][s.rank] = (unsigned long long)share_items;
+                    p.bal.peer_stats[q][(kMaxPeers + 1) + s.rank] = ns;
+                }
+            }
+            __threadfence_system();
+            for (int q = 0; q < s.world; ++q)
+                if (q != s.rank)
+                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(s.signal_flags[q] + s.rank), "l"(s.signal_value) : "memory");
+        }
+    }
+}
 
 // geometry helpers shared by host and device ---------------------------------------------------------
 __host__ __device__ inline int sym_tiles_in_block(long long n_total, int iblk, int tile, int K) {
@@ -122,11 +201,6 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
     float* jpart = reinterpret_cast<float*>(ssum + (size_t)3 * R * THREADS);       // [2][NWARPS][3][TILE]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long total = p.item_hi - p.item_lo;
-    const long long S = gridDim.x;
-    const long long lo = p.item_lo + sk_lo(total, blockIdx.x, S), hi = p.item_lo + sk_lo(total, blockIdx.x + 1, S);
-    if (lo >= hi) { peer_signal(p.sync); return; }   // CTA-uniform; an idle CTA still counts as done
-    const int ntiles = (int)(hi - lo);
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NWARPS); }
@@ -137,6 +211,13 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
     // several shards: the peers' integrate kernels of the previous step have stored their r' into this GPU's
     // position buffer and zeroed their rows of this GPU's accumulator — only then may this sweep read / add
     if (p.sync.wait_flags) peer_wait(p.sync);
+    long long share_lo, share_hi;
+    sym_share(p, share_lo, share_hi);
+    const long long total = share_hi - share_lo;
+    const long long S = gridDim.x;
+    const long long lo = share_lo + sk_lo(total, blockIdx.x, S), hi = share_lo + sk_lo(total, blockIdx.x + 1, S);
+    if (lo >= hi) { sym_finish(p, total); return; }   // CTA-uniform; an idle CTA still counts as done
+    const int ntiles = (int)(hi - lo);
 
     unsigned long long clk0 = 0, ns0 = 0;
     if (p.clk && tid == 0) {   // every CTA: start/end time stamps (debug: distribution of CTA lifetimes)
@@ -421,7 +502,7 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
         if (blockIdx.x == 0) { p.clk[0] = clock64() - clk0; p.clk[1] = ns1 - ns0; }
         if (blockIdx.x < 1016) { p.clk[2 + 2 * blockIdx.x] = ns0; p.clk[3 + 2 * blockIdx.x] = ns1; }
     }
-    peer_signal(p.sync);   // several shards: "my sweep is done" once every CTA has got here
+    sym_finish(p, total);   // several shards: "my sweep is done" once every CTA has got here
 }
 
 template <int THREADS, int R, int TILE, int STAGES>
@@ -455,11 +536,6 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
     double* jpart = reinterpret_cast<double*>(jbar + 1);             // [2][NWARPS][3][TILE]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long total = p.item_hi - p.item_lo;
-    const long long S = gridDim.x;
-    const long long lo = p.item_lo + sk_lo(total, blockIdx.x, S), hi = p.item_lo + sk_lo(total, blockIdx.x + 1, S);
-    if (lo >= hi) { peer_signal(p.sync); return; }   // CTA-uniform; an idle CTA still counts as done
-    const int ntiles = (int)(hi - lo);
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NWARPS); }
@@ -468,6 +544,13 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
     }
     __syncthreads();
     if (p.sync.wait_flags) peer_wait(p.sync);   // as in the fp32 kernel
+    long long share_lo, share_hi;
+    sym_share(p, share_lo, share_hi);
+    const long long total = share_hi - share_lo;
+    const long long S = gridDim.x;
+    const long long lo = share_lo + sk_lo(total, blockIdx.x, S), hi = share_lo + sk_lo(total, blockIdx.x + 1, S);
+    if (lo >= hi) { sym_finish(p, total); return; }
+    const int ntiles = (int)(hi - lo);
 
     unsigned long long clk0 = 0, ns0 = 0;
     if (p.clk && blockIdx.x == 0 && tid == 0) {
@@ -670,7 +753,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
         p.clk[0] = clock64() - clk0;
         p.clk[1] = ns1 - ns0;
     }
-    peer_signal(p.sync);
+    sym_finish(p, total);
 }
 
 template <int THREADS, int TILE, int STAGES>

@@ -126,8 +126,10 @@ int gravb200_partition(int64_t n_total, int dtype, int world, int rank, int64_t*
  * observed over its lifetime (clock64 / globaltimer), ms[4] = that lifetime in ms; several shards with the
  * symmetric sweep, last step that was followed by stage2 / ended a gravb200_steps call: ms[5] = sweep kernel,
  * ms[6] = integrate kernel (begins by waiting for every shard's sweep; peer loads of the partial sums, peer
- * stores of r' and of the cleared sums), ms[7] = tail wait for every shard's integrate; entries that do not
- * apply are -1; n = capacity of ms. */
+ * stores of r' and of the cleared sums), ms[7] = tail wait for every shard's integrate, ms[8] = this shard's
+ * share of the universe's tile list in that sweep relative to the equal share (speed-proportional shares: the
+ * shards publish items / ns of every sweep and cut the next one accordingly; GRAVB200_BALANCE=0 disables);
+ * entries that do not apply are -1; n = capacity of ms. */
 int gravb200_timings(gravb200_ctx* ctx, float* ms, int n);
 
 /* Introspection used by bench.py / tests: launch geometry and counters.

@@ -576,8 +576,8 @@ def test_sass_of_the_default_kernels(shim):
 		ins = funcs[names[0]]
 		return collections.Counter(i.split()[0].split('.')[0] for i in ins), ins
 	for key, must, bars in (
-		('sym_sweep_kernelILi256ELi12ELi512ELi3ELi2E', ('UBLKCP', 'FFMA2', 'FADD2', 'FMUL2', 'MUFU', 'SHFL', 'REDG', 'VOTE'), 4), # fp32 symmetric, variant 100
-		('sym_sweep_kernel_f64ILi256ELi8ELi256ELi3ELi1ELi1E', ('UBLKCP', 'DFMA', 'MUFU', 'SHFL', 'REDG', 'VOTE'), 4), # fp64 symmetric, variant 101
+		('sym_sweep_kernelILi256ELi12ELi512ELi3ELi2E', ('UBLKCP', 'FFMA2', 'FADD2', 'FMUL2', 'MUFU', 'SHFL', 'REDG', 'VOTE'), 6), # fp32 symmetric, variant 100
+		('sym_sweep_kernel_f64ILi256ELi8ELi256ELi3ELi1ELi1E', ('UBLKCP', 'DFMA', 'MUFU', 'SHFL', 'REDG', 'VOTE'), 6), # fp64 symmetric, variant 101
 		('sweep_kernelIfLi256ELi8ELi512ELi3ELi1ELi1ELi4ELi1E', ('UBLKCP', 'FFMA2', 'FADD2', 'FMUL2', 'MUFU', 'VOTE'), None), # fp32 ordered, variant 0
 		('sweep_kernelIdLi256ELi2ELi256ELi3ELi2ELi0ELi4ELi0E', ('UBLKCP', 'DFMA', 'MUFU', 'VOTE'), None), # fp64 ordered, variant 0
 		('small_steps_kernelIfLi256ELi4ELi4E', ('UBLKCP', 'FFMA2', 'FADD2', 'FMUL2', 'MUFU', 'VOTE', 'ATOMG', 'SHFL'), None), # fp32 persistent small-N, variant 200
@@ -591,7 +591,7 @@ def test_sass_of_the_default_kernels(shim):
 		assert any('PHASECHK' in i for i in ins) and not any('TRYWAIT' in i for i in ins), (key, 'mbarrier waits must be non-blocking probes')
 		assert any(i.startswith('MUFU.RSQ') for i in ins)
 		if bars is not None:
-			# mbarrier initialisation, the wait for the peers' flags at the start, the hand-over to the peers at the
+			# mbarrier initialisation, the wait for the peers' flags and the share of the tile list at the start, the hand-over to the peers at the
 			# end (twice: idle CTAs leave early) — none of them inside the sweep loop
 			# (ncu: smsp__average_warps_issue_stalled_barrier = 0 in profiles/r0*_ncu_sym_*_summary.md)
 			assert 1 <= ops['BAR'] <= bars, (key, ops['BAR'])
