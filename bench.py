@@ -70,7 +70,10 @@ class ClockSampler:
 		0x80: 'hw_power_brake_slowdown', 0x2: 'applications_clocks_setting', 0x10: 'sync_boost',
 		}
 
-	def __init__(self, index):
+	def __init__(self, index, period = 0.05):
+		# long steps are sampled at 4 Hz, short ones at 20 Hz: enough samples in either case, and fewer NVML queries
+		# next to the launches of a step (single multi-GPU steps showed millisecond outliers, cause not pinned down)
+		self.period = period
 		self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
 		self._stop = threading.Event()
 		try:
@@ -94,7 +97,7 @@ class ClockSampler:
 						self.reasons.add(name)
 			except Exception:
 				pass
-			self._stop.wait(0.05)
+			self._stop.wait(self.period)
 
 	def __enter__(self):
 		if self.ok:
@@ -257,7 +260,7 @@ def device_leg(env, n, dtype, steps, warmup, parity_rows):
 	env.sync()
 	wall0 = time.perf_counter()
 	step_ms, sweep_ms, xchg_ms, sm_mhz, phases = [], [], [], [], []
-	with ClockSampler(env.local_rank) as clocks:
+	with ClockSampler(env.local_rank, period = 0.25 if n >= (1 << 18) else 0.05) as clocks:
 		for _ in range(steps):
 			ms, t = one_step()
 			step_ms.append(ms); sweep_ms.append(t['sweep_ms']); xchg_ms.append(max(t['exchange_ms'], 0.0)); sm_mhz.append(t['sm_mhz'])
@@ -478,6 +481,7 @@ def own_arm(args):
 			},
 		'per_gpu': {'g_inter_s': per_gpu_rate, 'rows_rank0': int(main['rows']), 'rows_even_share': -(-n // world),
 			'sweep_ms': float(np.mean(main['sweep_ms'])), 'exchange_ms': float(np.mean(main['xchg_ms'])),
+			'step_ms_rank0': {'min': float(np.min(main['step_ms'])), 'median': float(np.median(main['step_ms'])), 'max': float(np.max(main['step_ms']))},
 			'sm_mhz_in_kernel': float(np.median(main['sm_mhz']))},
 		'wall_ms_per_step': main['wall_ms'] / args.steps,
 		'clocks': main['clocks'],

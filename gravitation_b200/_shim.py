@@ -345,6 +345,8 @@ class Shard:
 		out = dict(sweep_ms = ms[0], exchange_ms = ms[1], steps_ms = ms[2], sm_mhz = ms[3], cta0_ms = ms[4])
 		if ms[5] >= 0: # several shards, symmetric sweep: where the step's time went (the integrate kernel starts by waiting for every shard's sweep, the tail by waiting for every shard's integrate)
 			out['phases_ms'] = dict(sweep_kernel = ms[5], integrate_incl_wait_for_sweeps = ms[6], tail_wait = ms[7])
+			if ms[9] >= 0: # of the integrate kernel's time: the part after its wait for the peers' sweeps
+				out['phases_ms']['integrate_work'] = ms[9]
 			if ms[8] >= 0: # speed-proportional shares: this shard's part of the tile list against the equal share
 				out['phases_ms']['share_of_equal'] = ms[8]
 		return out

@@ -310,7 +310,7 @@ __global__ void unpack_kernel(const V4* __restrict__ in, REAL* out3, long long n
 }  // namespace
 
 // layout of a context's peer-visible flag array (u64 words): barrier generations | sweep done | integrate done | sweep stats (items, ns)
-constexpr int kFlagsSweep = kMaxPeers + 1, kFlagsIntegrate = 2 * (kMaxPeers + 1), kFlagsBalance = 3 * (kMaxPeers + 1), kFlagsTotal = 5 * (kMaxPeers + 1);
+constexpr int kFlagsSweep = kMaxPeers + 1, kFlagsIntegrate = 2 * (kMaxPeers + 1), kFlagsBalance = 3 * (kMaxPeers + 1), kFlagsTotal = 6 * (kMaxPeers + 1);
 
 struct gravb200_ctx {
     int dtype = 0, device = 0, rank = 0, world = 1;
@@ -447,7 +447,7 @@ int setup_sym(gravb200_ctx* c, int sv) {
     const char* bal_env = getenv("GRAVB200_BALANCE");
     c->sym_balance = c->world > 1 && (c->sym_hi - c->sym_lo) >= 16LL * c->grid && !(bal_env && bal_env[0] == '0');
     if (c->world > 1)   // a new variant counts tiles of another size: forget the published speeds
-        CU(cudaMemsetAsync(c->flags + kFlagsBalance, 0, 2 * (kMaxPeers + 1) * sizeof(unsigned long long), c->stream));
+        CU(cudaMemsetAsync(c->flags + kFlagsBalance, 0, 3 * (kMaxPeers + 1) * sizeof(unsigned long long), c->stream));
     c->use_sym = true;
     return 0;
 }
@@ -673,6 +673,7 @@ int launch_sweep(gravb200_ctx* c, int integrate) {
         ip.sp.T = c->T;
         ip.sp.integrate = integrate;
         ip.sp.n_peers = 0;
+        ip.sp.clk = c->clk;   // [2048], [2049]: end of the wait for the peers' sweeps, latest CTA end (several shards)
         ip.acc64 = c->acc64;
         ip.n_src = 0;
         if (multi) {
@@ -1159,7 +1160,7 @@ int gravb200_ctx_create(int64_t n_total, int dtype, int device, int rank, int wo
     CUX(cudaMemsetAsync(c->acc, 0, (size_t)c->chunk * v4, c->stream));
     CUX(cudaMalloc(&c->stage3, (size_t)n_total * 3 * c->esz));
     CUX(cudaMalloc(&c->stagem, (size_t)n_total * c->esz));
-    CUX(cudaMalloc(&c->clk, 2048 * sizeof(unsigned long long)));   // [0..1] CTA 0 cycles/ns, then per-CTA start/end stamps
+    CUX(cudaMalloc(&c->clk, 4096 * sizeof(unsigned long long)));   // [0..1] CTA 0 cycles/ns, then per-CTA start/end stamps
     CUX(cudaMalloc(&c->flags, kFlagsTotal * sizeof(unsigned long long)));
     CUX(cudaMemsetAsync(c->flags, 0, kFlagsTotal * sizeof(unsigned long long), c->stream));
     CUX(cudaMalloc(&c->done_ctr, 2 * sizeof(unsigned int)));
@@ -1172,7 +1173,7 @@ int gravb200_ctx_create(int64_t n_total, int dtype, int device, int rank, int wo
     }
     CUX(cudaMalloc(&c->xerr, sizeof(int)));
     CUX(cudaMemsetAsync(c->xerr, 0, sizeof(int), c->stream));
-    CUX(cudaMemsetAsync(c->clk, 0, 2048 * sizeof(unsigned long long), c->stream));
+    CUX(cudaMemsetAsync(c->clk, 0, 4096 * sizeof(unsigned long long), c->stream));
 #undef CUX
     if (world > 1) {
         int rc = nccl_load();
@@ -1441,9 +1442,15 @@ int gravb200_timings(gravb200_ctx* c, float* ms, int n) {
         if (n > 4) ms[4] = (float)((double)h[1] * 1e-6);   // lifetime of CTA 0 of the last sweep, ms
         if (n > 7 && c->tev_ok && c->use_sym && c->world > 1 && cudaEventQuery(c->tev[3]) == cudaSuccess)
             for (int i = 0; i < 3; ++i) CU(cudaEventElapsedTime(&ms[5 + i], c->tev[i], c->tev[i + 1]));
+        if (n > 9 && c->use_sym && c->world > 1) {   // the integrate kernel's own work, after its wait for the peers' sweeps
+            unsigned long long st[2] = {0, 0};
+            CU(cudaMemcpy(st, c->clk + 2048, sizeof(st), cudaMemcpyDeviceToHost));
+            if (st[0] && st[1] > st[0]) ms[9] = (float)((double)(st[1] - st[0]) * 1e-6);
+            CU(cudaMemset(c->clk + 2048, 0, sizeof(st)));
+        }
         if (n > 8 && c->use_sym && c->world > 1 && c->sym_balance) {   // this shard's share of the last sweep against the equal share
             unsigned long long items = 0;
-            CU(cudaMemcpy(&items, c->flags + kFlagsBalance + c->rank, sizeof(items), cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(&items, c->flags + kFlagsBalance + 2 * (kMaxPeers + 1) + c->rank, sizeof(items), cudaMemcpyDeviceToHost));
             if (items && c->sym_total > 0) ms[8] = (float)((double)items * c->world / (double)c->sym_total);
         }
 #ifdef SYM_DEBUG

@@ -50,7 +50,7 @@ namespace gravb200 {
 // on the boundaries without a host round trip.  The GPUs of one box differ by ~0.5 % under this load, and a step
 // takes as long as its slowest sweep (profiles/r02_bench_n8*.json: rank 0's sweep 37.77 / 37.94 ms on two boxes).
 struct SymBalance {
-    const unsigned long long* stats;                  // local [2][kMaxPeers + 1]: items, ns of every shard's previous sweep; nullptr: equal shares
+    const unsigned long long* stats;                  // local [3][kMaxPeers + 1]: items, ns per shard (published speeds) and, [2][rank], the share of the last sweep; nullptr: equal shares
     unsigned long long* peer_stats[kMaxPeers + 1];    // that array on every shard (entries [rank] are ours to write)
     unsigned long long* tstart;                       // local: earliest CTA start of this launch
 };
@@ -75,36 +75,42 @@ struct SymParams {
     SymBalance bal;               // several shards, long sweeps: speed-proportional shares instead of [item_lo, item_hi)
 };
 
+// Shard `me`'s share [lo, hi) of `total` flat items from the published (items, ns) of every shard's previous sweep
+// (stats[q], stats[kMaxPeers + 1 + q]); any missing entry keeps the equal shares [eq_lo, eq_hi).  Every shard runs
+// the same additions in the same order, so hi of shard r and lo of shard r + 1 are the same number: the shares
+// tile [0, total) without gaps or overlaps (tests/native/sym_schedule_check.cu).  Two passes, no array.
+__host__ __device__ inline void sym_share_bounds(long long total, int P, int me, const unsigned long long* stats,
+                                                 long long eq_lo, long long eq_hi, long long& lo, long long& hi) {
+    auto weight = [&](int q) -> double {
+        const unsigned long long items = stats[q], ns = stats[(kMaxPeers + 1) + q];
+        return (items == 0 || ns == 0) ? 0.0 : (double)items / (double)ns;
+    };
+    double sum = 0.0, c0 = 0.0;
+    bool ok = true;
+    for (int q = 0; q < P; ++q) {
+        const double wq = weight(q);
+        if (wq == 0.0) ok = false;
+        if (q == me) c0 = sum;
+        sum += wq;
+    }
+    lo = eq_lo; hi = eq_hi;
+    if (!ok) return;
+    const double c1 = c0 + weight(me);
+    lo = me == 0 ? 0 : (long long)((double)total * (c0 / sum));
+    hi = me == P - 1 ? total : (long long)((double)total * (c1 / sum));
+    if (lo > total) lo = total;
+    if (hi > total) hi = total;
+    if (hi < lo) hi = lo;
+}
+
 // this launch's share of the flat list; all threads call it (CTA barrier inside when balancing)
 __device__ __forceinline__ void sym_share(const SymParams& p, long long& share_lo, long long& share_hi) {
     share_lo = p.item_lo; share_hi = p.item_hi;
     if (p.bal.stats == nullptr) return;
     __shared__ long long s_share[2];
     if (threadIdx.x == 0) {
-        const int P = p.sync.world, me = p.sync.rank;
-        const long long total = p.row_start[p.n_iblocks];
-        // weight of shard q = items / ns of its previous sweep; two passes instead of an array (no local memory)
-        auto weight = [&](int q) -> double {
-            const unsigned long long items = p.bal.stats[q], ns = p.bal.stats[(kMaxPeers + 1) + q];
-            return (items == 0 || ns == 0) ? 0.0 : (double)items / (double)ns;
-        };
-        double sum = 0.0, c0 = 0.0;
-        bool ok = true;
-        for (int q = 0; q < P; ++q) {   // the same additions in the same order on every shard
-            const double wq = weight(q);
-            if (wq == 0.0) ok = false;
-            if (q == me) c0 = sum;
-            sum += wq;
-        }
-        long long lo = p.item_lo, hi = p.item_hi;
-        if (ok) {
-            const double c1 = c0 + weight(me);
-            lo = me == 0 ? 0 : (long long)((double)total * (c0 / sum));
-            hi = me == P - 1 ? total : (long long)((double)total * (c1 / sum));
-            if (lo > total) lo = total;
-            if (hi > total) hi = total;
-            if (hi < lo) hi = lo;
-        }
+        long long lo, hi;
+        sym_share_bounds(p.row_start[p.n_iblocks], p.sync.world, p.sync.rank, p.bal.stats, p.item_lo, p.item_hi, lo, hi);
         s_share[0] = lo; s_share[1] = hi;
         unsigned long long now;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -129,10 +135,20 @@ __device__ __forceinline__ void sym_finish(const SymParams& p, long long share_i
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
                 const unsigned long long t0 = atomicExch(p.bal.tstart, ~0ull);   // earliest start of this launch; reset for the next
                 const unsigned long long ns = now > t0 ? now - t0 : 0ull;
-                for (int q = 0; q < s.world; ++q) {
-                    p.bal.peer_stats[q][s.rank] = (unsigned long long)share_items;
-                    p.bal.peer_stats[q][(kMaxPeers + 1) + s.rank] = ns;
+                // published speed = 10^6 items per `best` ns, best = the FASTEST sweep seen so far, relaxed by 0.05 % per
+                // step: a hiccup inside one sweep (they only ever add time: +1 % on single steps, r02k_bench_n2_*.json)
+                // must not move work away from a healthy GPU, a GPU that really slows down is followed within ~10 steps
+                unsigned long long best = 0;
+                if (share_items > 0 && ns > 0) {
+                    best = ns * 1000000ull / (unsigned long long)share_items;
+                    const unsigned long long prev = p.bal.stats[(kMaxPeers + 1) + s.rank];
+                    if (prev) best = min(best, prev + (prev >> 11) + 1);
                 }
+                for (int q = 0; q < s.world; ++q) {
+                    p.bal.peer_stats[q][s.rank] = best ? 1000000ull : 0ull;
+                    p.bal.peer_stats[q][(kMaxPeers + 1) + s.rank] = best;
+                }
+                p.bal.peer_stats[s.rank][2 * (kMaxPeers + 1) + s.rank] = (unsigned long long)share_items;   // local: the share this sweep had
             }
             __threadfence_system();
             for (int q = 0; q < s.world; ++q)
@@ -782,6 +798,11 @@ __global__ void sym_integrate_kernel(const IntegrateParams q) {
     using V4 = typename Vec4<REAL>::type;
     const long long il = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (q.sync.wait_flags) peer_wait(q.sync);   // every shard's sweep of this step is complete
+    if (q.sp.clk && q.sync.wait_flags && blockIdx.x == 0 && threadIdx.x == 0) {   // when the wait ended (gravb200_timings: wait vs work of this kernel)
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        q.sp.clk[2048] = t;
+    }
     if (il < q.sp.n_local) {
         double sx, sy, sz;
         if (q.n_src == 0) {
@@ -808,6 +829,11 @@ __global__ void sym_integrate_kernel(const IntegrateParams q) {
         }
         const V4 ri = reinterpret_cast<const V4*>(q.sp.pos_front)[q.sp.row0 + il];
         finalize_body(q.sp, il, sx, sy, sz, ri, REAL(0));
+    }
+    if (q.sp.clk && q.sync.wait_flags && threadIdx.x == 0) {   // latest CTA end
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMax(q.sp.clk + 2049, t);
     }
     peer_signal(q.sync);
 }

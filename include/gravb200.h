@@ -128,7 +128,8 @@ int gravb200_partition(int64_t n_total, int dtype, int world, int rank, int64_t*
  * ms[6] = integrate kernel (begins by waiting for every shard's sweep; peer loads of the partial sums, peer
  * stores of r' and of the cleared sums), ms[7] = tail wait for every shard's integrate, ms[8] = this shard's
  * share of the universe's tile list in that sweep relative to the equal share (speed-proportional shares: the
- * shards publish items / ns of every sweep and cut the next one accordingly; GRAVB200_BALANCE=0 disables);
+ * shards publish items / ns of every sweep and cut the next one accordingly; GRAVB200_BALANCE=0 disables),
+ * ms[9] = the part of ms[6] after the wait (the integrate kernel's own work);
  * entries that do not apply are -1; n = capacity of ms. */
 int gravb200_timings(gravb200_ctx* ctx, float* ms, int n);
 

@@ -9,6 +9,7 @@
 //      end of the last local row, whatever flat offset a CTA starts from (binary search + walk, as in the kernel),
 //   4. the j-tiles of a row cover its column blocks completely (ragged last block included),
 //   5. block rows carry equal work up to one column block (load balance across shards).
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -126,9 +127,45 @@ void check_stream_k(long long& cases) {
         }
 }
 
+// speed-proportional shares of the flat list (sym_share_bounds): for random published (items, ns) the P shares tile
+// [0, total) exactly — every shard computes its own bounds, hi of shard r must BE lo of shard r + 1 — follow the
+// speeds (items / ns) to one item, and fall back to the equal shares while any shard has not published yet
+static void check_shares(long long& cases) {
+    unsigned long long seed = 12345;
+    auto rnd = [&]() { seed = seed * 6364136223846793005ull + 1442695040888963407ull; return seed >> 33; };
+    for (int rep = 0; rep < 4000; ++rep) {
+        const int P = 1 + (int)(rnd() % 16);
+        const long long total = 1 + (long long)(rnd() % 3000000);
+        unsigned long long stats[2 * (kMaxPeers + 1)] = {};
+        double speed[kMaxPeers + 1], sum = 0;
+        const bool missing = rep % 7 == 0;
+        for (int q = 0; q < P; ++q) {
+            stats[q] = 1 + rnd() % 100000;
+            stats[(kMaxPeers + 1) + q] = 1000000 + rnd() % 40000000;
+            speed[q] = (double)stats[q] / (double)stats[(kMaxPeers + 1) + q];
+            sum += speed[q];
+        }
+        if (missing) stats[rnd() % P] = 0;
+        long long prev_hi = 0;
+        for (int me = 0; me < P; ++me) {
+            long long lo, hi;
+            const long long eq_lo = sk_lo(total, me, P), eq_hi = sk_lo(total, me + 1, P);
+            sym_share_bounds(total, P, me, stats, eq_lo, eq_hi, lo, hi);
+            CHECK(lo == prev_hi, "share %d of %d starts at %lld, the previous one ended at %lld", me, P, lo, prev_hi);
+            CHECK(hi >= lo && hi <= total, "share %d: [%lld, %lld) of %lld", me, lo, hi, total);
+            if (missing) CHECK(lo == eq_lo && hi == eq_hi, "a shard has not published: equal shares expected");
+            else CHECK(std::abs((double)(hi - lo) - (double)total * speed[me] / sum) <= 2.0, "share %d is %lld items, its speed asks for %.1f", me, hi - lo, (double)total * speed[me] / sum);
+            prev_hi = hi;
+        }
+        CHECK(prev_hi == total, "the shares end at %lld of %lld", prev_hi, total);
+        ++cases;
+    }
+}
+
 int main() {
     long long cases = 0;
     check_stream_k(cases);
+    check_shares(cases);
     sweep<3072, 512>(cases); sweep<3072, 256>(cases); sweep<2048, 512>(cases); sweep<2048, 256>(cases);
     sweep<1024, 256>(cases); sweep<1536, 256>(cases); sweep<1536, 128>(cases); sweep<1024, 128>(cases);
     printf("%s: %lld cases, %lld failed checks\n", fails ? "FAILED" : "OK", cases, fails);
