@@ -58,6 +58,7 @@ _SIGNATURES = [
 	('gravb200_timings', ctypes.c_int, [_c_ctx, ctypes.POINTER(ctypes.c_float), ctypes.c_int]),
 	('gravb200_info', ctypes.c_int, [_c_ctx, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
 	('gravb200_set_variant', ctypes.c_int, [_c_ctx, ctypes.c_int]),
+	('gravb200_set_split', ctypes.c_int, [_c_ctx, ctypes.c_int]),
 	('gravb200_variant_count', ctypes.c_int, [ctypes.c_int]),
 	('gravb200_sym_variant_count', ctypes.c_int, [ctypes.c_int]),
 	('gravb200_small_variant_count', ctypes.c_int, []),
@@ -352,9 +353,9 @@ class Shard:
 		return out
 
 	def info(self):
-		v = (ctypes.c_int64 * 12)()
-		_check(self._lib.gravb200_info(self._ctx, v, 12))
-		keys = ('grid', 'threads', 'bodies_per_thread', 'tile', 'stages', 'smem_bytes', 'launches', 'sm_count', 'packed', 'ctas_per_sm', 'exchange_mode', 'variant')
+		v = (ctypes.c_int64 * 13)()
+		_check(self._lib.gravb200_info(self._ctx, v, 13))
+		keys = ('grid', 'threads', 'bodies_per_thread', 'tile', 'stages', 'smem_bytes', 'launches', 'sm_count', 'packed', 'ctas_per_sm', 'exchange_mode', 'variant', 'split')
 		return dict(zip(keys, [int(x) for x in v]))
 
 	def peer_barrier(self):
@@ -363,6 +364,10 @@ class Shard:
 
 	def set_variant(self, variant):
 		_check(self._lib.gravb200_set_variant(self._ctx, int(variant)))
+
+	def set_split(self, mode):
+		"""symmetric sweeps: CTA ranges cut at chunk (1) or tile (0) granularity, -1 = automatic"""
+		_check(self._lib.gravb200_set_split(self._ctx, int(mode)))
 
 	def device_ptr(self, which):
 		return self._lib.gravb200_device_ptr(self._ctx, which)

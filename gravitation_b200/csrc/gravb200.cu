@@ -171,32 +171,36 @@ struct SymVariant {
     int threads, r, tile, stages;
     size_t smem;
     const void* fn;
+    const void* fn_split;   // the same kernel with CTA ranges cut at chunk (32 j-bodies) instead of tile granularity; nullptr: not built
 };
-template <int THREADS, int R, int TILE, int STAGES, int UNROLL>
+template <int THREADS, int R, int TILE, int STAGES, int UNROLL, bool WITH_SPLIT>
 SymVariant make_sym(const char* name) {
     SymVariant v;
     v.name = name;
     v.threads = THREADS; v.r = R; v.tile = TILE; v.stages = STAGES;
     v.smem = sym_smem_bytes<THREADS, R, TILE, STAGES>();
-    v.fn = (const void*)&sym_sweep_kernel<THREADS, R, TILE, STAGES, UNROLL>;
+    v.fn = (const void*)&sym_sweep_kernel<THREADS, R, TILE, STAGES, UNROLL, 0>;
+    v.fn_split = nullptr;
+    if constexpr (WITH_SPLIT) v.fn_split = (const void*)&sym_sweep_kernel<THREADS, R, TILE, STAGES, UNROLL, 1>;
     return v;
 }
-#define VSYM(T, R, TILE, ST, U) make_sym<T, R, TILE, ST, U>("f32sym_t" #T "_r" #R "_j" #TILE "_s" #ST "_u" #U)
+#define VSYM(T, R, TILE, ST, U) make_sym<T, R, TILE, ST, U, false>("f32sym_t" #T "_r" #R "_j" #TILE "_s" #ST "_u" #U)
+#define VSYMS(T, R, TILE, ST, U) make_sym<T, R, TILE, ST, U, true>("f32sym_t" #T "_r" #R "_j" #TILE "_s" #ST "_u" #U)   // + split twin
 constexpr int kSymBase = 100;
 const std::vector<SymVariant>& variants_sym() {
     static const std::vector<SymVariant> v = {
-        VSYM(256, 12, 512, 3, 2),   // 100 auto: N >= 65536 on one GPU (IBLK 3072)
-        VSYM(256, 8, 512, 3, 4),    // 101 auto: 16384 <= N < 65536; power-of-two IBLK 2048 (shards of several GPUs)
-        VSYM(256, 8, 256, 3, 2),    // 102
+        VSYMS(256, 12, 512, 3, 2),  // 100 auto: N >= 65536 on one GPU (IBLK 3072)
+        VSYMS(256, 8, 512, 3, 4),   // 101 auto: 16384 <= N < 65536; power-of-two IBLK 2048 (shards of several GPUs)
+        VSYMS(256, 8, 256, 3, 2),   // 102
         VSYM(256, 8, 512, 3, 2),    // 103
         VSYM(256, 8, 512, 3, 1),    // 104
         VSYM(256, 10, 512, 3, 2),   // 105
-        VSYM(128, 8, 256, 3, 2),    // 106 auto: 8192 <= N < 16384 (IBLK 1024)
+        VSYMS(128, 8, 256, 3, 2),   // 106 auto: 8192 <= N < 16384 (IBLK 1024)
         VSYM(256, 6, 512, 3, 2),    // 107
         VSYM(256, 12, 512, 3, 1),   // 108
         VSYM(256, 12, 512, 3, 4),   // 109
         VSYM(256, 14, 512, 3, 2),   // 110
-        VSYM(256, 12, 256, 3, 2),   // 111
+        VSYMS(256, 12, 256, 3, 2),  // 111
         VSYM(256, 8, 256, 3, 4),    // 112
         VSYM(256, 10, 256, 3, 2),   // 113
         VSYM(256, 16, 512, 3, 1),   // 114
@@ -208,28 +212,31 @@ const std::vector<SymVariant>& variants_sym() {
     return v;
 }
 
-template <int THREADS, int R, int TILE, int STAGES, int MINB, int UNROLL>
+template <int THREADS, int R, int TILE, int STAGES, int MINB, int UNROLL, bool WITH_SPLIT>
 SymVariant make_sym64(const char* name) {
     SymVariant v;
     v.name = name;
     v.threads = THREADS; v.r = R; v.tile = TILE; v.stages = STAGES;
     v.smem = sym64_smem_bytes<THREADS, TILE, STAGES>();
-    v.fn = (const void*)&sym_sweep_kernel_f64<THREADS, R, TILE, STAGES, MINB, UNROLL>;
+    v.fn = (const void*)&sym_sweep_kernel_f64<THREADS, R, TILE, STAGES, MINB, UNROLL, 0>;
+    v.fn_split = nullptr;
+    if constexpr (WITH_SPLIT) v.fn_split = (const void*)&sym_sweep_kernel_f64<THREADS, R, TILE, STAGES, MINB, UNROLL, 1>;
     return v;
 }
-#define VSYM64(T, R, TILE, ST, MB, U) make_sym64<T, R, TILE, ST, MB, U>("f64sym_t" #T "_r" #R "_j" #TILE "_s" #ST "_b" #MB "_u" #U)
+#define VSYM64(T, R, TILE, ST, MB, U) make_sym64<T, R, TILE, ST, MB, U, false>("f64sym_t" #T "_r" #R "_j" #TILE "_s" #ST "_b" #MB "_u" #U)
+#define VSYM64S(T, R, TILE, ST, MB, U) make_sym64<T, R, TILE, ST, MB, U, true>("f64sym_t" #T "_r" #R "_j" #TILE "_s" #ST "_b" #MB "_u" #U)
 const std::vector<SymVariant>& variants_sym64() {
     static const std::vector<SymVariant> v = {
         VSYM64(256, 6, 256, 3, 1, 2),   // 100 (IBLK 1536)
-        VSYM64(256, 8, 256, 3, 1, 1),   // 101 auto: N >= 2^14 on one GPU and on shards of several GPUs (IBLK 2048)
-        VSYM64(256, 4, 128, 3, 2, 2),   // 102 auto: medium N (IBLK 1024)
+        VSYM64S(256, 8, 256, 3, 1, 1),  // 101 auto: N >= 2^14 on one GPU and on shards of several GPUs (IBLK 2048)
+        VSYM64S(256, 4, 128, 3, 2, 2),  // 102 auto: medium N (IBLK 1024)
         VSYM64(256, 4, 256, 3, 2, 2),   // 103
         VSYM64(256, 4, 256, 3, 2, 1),   // 104
         VSYM64(256, 2, 256, 3, 2, 2),   // 105
         VSYM64(128, 4, 128, 3, 4, 2),   // 106
         VSYM64(256, 6, 256, 3, 1, 1),   // 107
         VSYM64(256, 6, 128, 3, 1, 2),   // 108
-        VSYM64(256, 8, 128, 3, 1, 1),   // 109
+        VSYM64S(256, 8, 128, 3, 1, 1),  // 109
         VSYM64(256, 8, 256, 3, 1, 2),   // 110
     };
     return v;
@@ -273,6 +280,7 @@ constexpr long long kSmallAutoMaxN = 12800;   // fp32, four row groups per CTA: 
 // of the whole universe is cut into one equal range per shard (stream-K across GPUs, setup_sym), so no block
 // alignment is needed and every N keeps the fastest variant.  (Round 1 rounded the shards up to whole blocks:
 // +0.8 % rows on seven of eight GPUs at N = 2^20.)
+constexpr long long kSplitGainPct = 3;   // whole-tile imbalance (slowest CTA over the average, %) from which the chunk-granular twin pays
 constexpr int64_t kSymShardMinN = 32768;   // automatic choice on several shards: symmetric sweep from this N on
 int64_t shard_chunk(int64_t n_total, int world, int /*dtype*/) {
     return (n_total + world - 1) / world;
@@ -362,6 +370,8 @@ struct gravb200_ctx {
     long long* row_start = nullptr;
     size_t row_start_n = 0;
     bool use_sym = false;
+    int split_mode = -1;           // CTA ranges of the symmetric sweep at chunk granularity: -1 automatic, 0 never, 1 wherever the variant has the twin
+    bool sym_split = false;        // what the current set-up uses
     long long sym_min_n = 8192;    // automatic choice: symmetric sweep from this N on
     int sym_variant = 0, sym_blocks = 0, sym_gblocks = 0;
     long long sym_total = 0, sym_lo = 0, sym_hi = 0;   // flat items of the universe, this shard's share
@@ -441,7 +451,19 @@ int setup_sym(gravb200_ctx* c, int sv) {
     c->sym_lo = sk_lo(rs[nib], c->rank, c->world);
     c->sym_hi = sk_lo(rs[nib], c->rank + 1, c->world);
     c->occ = occ;
-    c->grid = (int)std::max<long long>(1, std::min<long long>((long long)occ * c->sm_count, c->sym_hi - c->sym_lo));
+    // Few tiles per CTA (mid-sized universes, small shards): cut the CTA ranges at chunk granularity, so the slowest
+    // CTA carries 1 / CHUNKS of a tile more than the average instead of up to a whole tile, and more CTAs than
+    // tiles can work (N = 24576 fp32: 277.6 -> 200.8 us per step, profiles/r02_split_ab.md).  The twin's ring loop
+    // is the same instructions in another order of ptxas' choosing and 1 - 2.6 % slower (N = 2^18: 19.19 -> 19.68 ms),
+    // so it is used where whole tiles leave the slowest CTA more than kSplitGainPct % above the average; the large
+    // universes keep the kernel that was profiled.
+    const long long share_tiles = c->sym_hi - c->sym_lo, slots = (long long)occ * c->sm_count;
+    const long long slowest = (share_tiles + slots - 1) / slots;   // tiles of the slowest CTA with whole-tile ranges
+    c->sym_split = v.fn_split != nullptr &&
+                   (c->split_mode == 1 || (c->split_mode < 0 && slowest * slots * 100 > share_tiles * (100 + kSplitGainPct)));
+    if (c->sym_split) CU(cudaFuncSetAttribute(v.fn_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
+    const long long units = c->sym_split ? share_tiles * (v.tile / 32) : share_tiles;
+    c->grid = (int)std::max<long long>(1, std::min<long long>(slots, units));
     // several shards with long sweeps (>= 16 tiles per CTA): the shares follow the measured speed of each GPU
     // (nbody_sym.cuh, SymBalance); GRAVB200_BALANCE=0 keeps the equal shares
     const char* bal_env = getenv("GRAVB200_BALANCE");
@@ -561,7 +583,7 @@ int pick_variant(gravb200_ctx* c) {
         if (c->forced_variant >= kSymBase) sv = c->forced_variant - kSymBase;
         else if (c->forced_variant < 0 && c->n_total >= c->sym_min_n)
             sv = c->dtype == GRAVB200_F32 ? (c->n_total >= 65536 ? 0 : (c->n_total > kSmallAutoMaxN ? 1 : 6))
-                                          : (c->n_total >= 16384 ? 1 : 2);   // profiles/r01_sym*_variants_sweep*.txt
+                                          : (c->n_total >= 10240 ? 1 : 2);   // profiles/r01_sym*_variants_sweep*.txt; fp64 with chunk-granular ranges: r02_split_ab.md
         if (sv >= 0) return setup_sym(c, sv);
     } else if (c->world > 1 && c->peer_mode && c->acc64) {
         int sv = -1;
@@ -710,7 +732,7 @@ int launch_sweep(gravb200_ctx* c, int integrate) {
         void* sargs[] = {&sp};
         const bool trace = multi && c->tev[0];
         if (trace) CU(cudaEventRecord(c->tev[0], c->stream));
-        CU(cudaLaunchKernel(sv.fn, dim3(c->grid), dim3(sv.threads), sargs, sv.smem, c->stream));
+        CU(cudaLaunchKernel(c->sym_split ? sv.fn_split : sv.fn, dim3(c->grid), dim3(sv.threads), sargs, sv.smem, c->stream));
         if (trace) CU(cudaEventRecord(c->tev[1], c->stream));
         const unsigned gb = (unsigned)std::max<long long>(1, (c->n_local + 255) / 256);
         if (c->dtype == GRAVB200_F32) sym_integrate_kernel<float><<<gb, 256, 0, c->stream>>>(ip);
@@ -1132,6 +1154,7 @@ int gravb200_ctx_create(int64_t n_total, int dtype, int device, int rank, int wo
     c->device = device;
     c->rank = rank;
     c->world = world;
+    if (const char* e = getenv("GRAVB200_SPLIT")) c->split_mode = e[0] == '0' ? 0 : (e[0] == '1' ? 1 : -1);   // A/B runs of unmodified callers
     c->n_total = n_total;
     c->chunk = shard_chunk(n_total, world, dtype);
     c->n_pad = c->chunk * world;
@@ -1468,7 +1491,8 @@ int gravb200_timings(gravb200_ctx* c, float* ms, int n) {
 
 int gravb200_info(const gravb200_ctx* c, int64_t* info, int n) {
     if (!c || !info) return fail(GRAVB200_EINVAL, "ctx / info is NULL");
-    int64_t vals[12];
+    int64_t vals[13];
+    vals[12] = c->use_sym && c->sym_split ? 1 : 0;
     if (c->use_small) {
         const SmallVariant& v = variants_small()[c->small_variant];
         const int64_t t[12] = {c->grid, v.threads, v.r, c->small_slice, 1, (int64_t)c->small_smem,
@@ -1485,7 +1509,7 @@ int gravb200_info(const gravb200_ctx* c, int64_t* info, int n) {
                                c->launches, c->sm_count, v.pack, c->occ, c->peer_mode ? 1 : 0, c->variant};
         memcpy(vals, t, sizeof(t));
     }
-    for (int i = 0; i < n && i < 12; ++i) info[i] = vals[i];
+    for (int i = 0; i < n && i < 13; ++i) info[i] = vals[i];
     return 0;
 }
 
@@ -1499,6 +1523,18 @@ int gravb200_set_variant(gravb200_ctx* c, int variant) {
     if (c->pending) return fail(GRAVB200_EINVAL, "cannot switch variant between stage1 and stage2");
     CU(cudaSetDevice(c->device));
     c->forced_variant = variant < 0 ? -1 : variant;
+    int rc = pick_variant(c);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int gravb200_set_split(gravb200_ctx* c, int mode) {
+    if (!c) return fail(GRAVB200_EINVAL, "ctx is NULL");
+    if (mode < -1 || mode > 1) return fail(GRAVB200_EINVAL, "split mode %d: -1 (automatic), 0 or 1", mode);
+    if (c->pending) return fail(GRAVB200_EINVAL, "cannot switch the split mode between stage1 and stage2");
+    CU(cudaSetDevice(c->device));
+    c->split_mode = mode;
     int rc = pick_variant(c);
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));

@@ -196,11 +196,39 @@ __host__ __device__ __forceinline__ void sym_advance(SymWalker& w, const SymPara
     }
 }
 
+// A CTA's range of the flat list.  SPLIT = 0: whole tiles, [lo, hi).  SPLIT = 1: the share is cut at CHUNK
+// granularity (32 j-bodies, the unit of the ring) — tiles [lo, hi), of which the first one starts at chunk
+// c_first and the last one ends before chunk c_last; two CTAs may then work on disjoint chunk ranges of the same
+// tile.  Mid-sized universes have only a few tiles per CTA (10.26 at N = 2^16 on 148 CTAs: the slowest CTA
+// carried 11), with chunks the imbalance is 1 / CHUNKS of that.  (tests/native/sym_schedule_check.cu replays it.)
+struct SymRange {
+    long long lo, hi;
+    int c_first, c_last;
+};
+template <int CHUNKS, int SPLIT>
+__host__ __device__ __forceinline__ bool sym_cta_range(long long share_lo, long long total, long long b, long long S, SymRange& rg) {
+    if (SPLIT) {
+        const long long tc = total * CHUNKS;
+        const long long lo_c = sk_lo(tc, b, S), hi_c = sk_lo(tc, b + 1, S);
+        if (lo_c >= hi_c) return false;
+        rg.lo = share_lo + lo_c / CHUNKS;
+        rg.c_first = (int)(lo_c % CHUNKS);
+        rg.hi = share_lo + (hi_c + CHUNKS - 1) / CHUNKS;
+        const int rem = (int)(hi_c % CHUNKS);
+        rg.c_last = rem ? rem : CHUNKS;
+        return true;
+    }
+    rg.lo = share_lo + sk_lo(total, b, S);
+    rg.hi = share_lo + sk_lo(total, b + 1, S);
+    rg.c_first = 0; rg.c_last = CHUNKS;
+    return rg.lo < rg.hi;
+}
+
 // ------------------------------------------------------------------------------------------------
 // THREADS threads, R i-bodies per thread (even), TILE j-bodies per TMA stage (multiple of 32), STAGES.
 // Dynamic shared memory: tile ring | mbarriers (full, empty, jbar) | fp64 i-sums [3][R][THREADS] | j-partials [2][NWARPS][3][TILE].
 // ------------------------------------------------------------------------------------------------
-template <int THREADS, int R, int TILE, int STAGES, int UNROLL>
+template <int THREADS, int R, int TILE, int STAGES, int UNROLL, int SPLIT = 0>
 __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p) {
     constexpr int IBLK = THREADS * R;
     constexpr int NWARPS = THREADS / 32;
@@ -231,9 +259,10 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
     sym_share(p, share_lo, share_hi);
     const long long total = share_hi - share_lo;
     const long long S = gridDim.x;
-    const long long lo = share_lo + sk_lo(total, blockIdx.x, S), hi = share_lo + sk_lo(total, blockIdx.x + 1, S);
-    if (lo >= hi) { sym_finish(p, total); return; }   // CTA-uniform; an idle CTA still counts as done
-    const int ntiles = (int)(hi - lo);
+    SymRange rg;
+    if (!sym_cta_range<CHUNKS, SPLIT>(share_lo, total, blockIdx.x, S, rg)) { sym_finish(p, total); return; }   // CTA-uniform; an idle CTA still counts as done
+    const long long lo = rg.lo;
+    const int ntiles = (int)(rg.hi - rg.lo);
 
     unsigned long long clk0 = 0, ns0 = 0;
     if (p.clk && tid == 0) {   // every CTA: start/end time stamps (debug: distribution of CTA lifetimes)
@@ -308,7 +337,7 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
     // ring round (32 steps) later, when all warps have long arrived, so no warp ever idles at a CTA barrier.
     // jpart is double buffered: a buffer is rewritten two tiles later, after the wait that follows its combine.
     bool jpend = false;
-    int jpend_n = 0, jpend_buf = 0;
+    int jpend_lo = 0, jpend_n = 0, jpend_buf = 0;   // j-bodies [jpend_lo, jpend_n) of the tile (SPLIT: the chunks this CTA evaluated)
     long long jpend_j0 = 0;
     uint32_t j_parity = 0;
     auto combine_pending = [&]() {
@@ -321,7 +350,7 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
 #endif
         j_parity ^= 1;
         const float* jb = jpart + (size_t)jpend_buf * NWARPS * 3 * TILE;
-        for (int j = tid; j < jpend_n; j += THREADS) {
+        for (int j = (SPLIT ? jpend_lo : 0) + tid; j < jpend_n; j += THREADS) {
             double sx = 0.0, sy = 0.0, sz = 0.0;
 #pragma unroll
             for (int wv = 0; wv < NWARPS; ++wv) {
@@ -378,6 +407,9 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
         long long cntl = p.n_total - j0;
         const int jn = cntl > TILE ? TILE : (int)cntl;
         const float e2 = p.eps2_f;
+        // SPLIT: the chunks [cb, ce) of this tile are this CTA's (all of them except in its first and last tile)
+        const int cb = (SPLIT && k == 0) ? rg.c_first : 0;
+        const int ce = (SPLIT && k == ntiles - 1) ? rg.c_last : CHUNKS;
 
         float2 ax[P], ay[P], az[P];
 #pragma unroll
@@ -406,12 +438,13 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
                     az[q] = __ffma2_rn(dz, sc, az[q]);
                 }
             };
-            if (jn == TILE) {
+            const int jbeg = cb * 32, jend = (SPLIT && ce * 32 < jn) ? ce * 32 : jn;
+            if (jbeg == 0 && jend == TILE) {
 #pragma unroll 2
                 for (int j = 0; j < TILE; ++j) ordered(tile[j], dj0 + j);
             } else {
 #pragma unroll 1
-                for (int j = 0; j < jn; ++j) ordered(tile[j], dj0 + j);
+                for (int j = jbeg; j < jend; ++j) ordered(tile[j], dj0 + j);
             }
             SYM_DIVCHK(3);
             __syncwarp();
@@ -422,7 +455,7 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
             // symmetric tile: ring over 32-body chunks
             float* jp = jpart + ((size_t)jbuf * NWARPS + warp) * 3 * TILE;
 #pragma unroll 1
-            for (int c = 0; c < CHUNKS; ++c) {
+            for (int c = cb; c < ce; ++c) {
                 const int jl = c * 32 + lane;
                 SYM_DIVCHK(10);
 #ifdef SYM_DEBUG
@@ -438,7 +471,7 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
                 // padding j-bodies sit at the opposite far corner from padding i-bodies, so d2 is never 0
                 float4 bj = make_float4(-1.0e30f, -1.0e30f, -1.0e30f, 0.f);
                 if (jl < jn) bj = tile[jl];
-                if (c == CHUNKS - 1) {   // last read of this ring slot
+                if (c == ce - 1) {   // last read of this ring slot
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty_bar[s]);
                 }
@@ -475,7 +508,7 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
                 }
                 SYM_DIVCHK(7);
                 // after 32 rotations every lane holds its own j-body again, with the sum over this warp's i-bodies
-                if (c == 0 && jpend) combine_pending();   // previous tile's j side (its buffer is the other one)
+                if (c == cb && jpend) combine_pending();   // previous tile's j side (its buffer is the other one)
                 jp[0 * TILE + jl] = -(jx.x + jx.y);
                 jp[1 * TILE + jl] = -(jy.x + jy.y);
                 jp[2 * TILE + jl] = -(jz.x + jz.y);
@@ -496,7 +529,7 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
             // j side: this warp's partials are in shared memory; the combine happens in the next tile
             __syncwarp();
             if (lane == 0) mbar_arrive(jbar);
-            jpend = true; jpend_n = jn; jpend_j0 = j0; jpend_buf = jbuf;
+            jpend = true; jpend_lo = cb * 32; jpend_n = (SPLIT && ce * 32 < jn) ? ce * 32 : jn; jpend_j0 = j0; jpend_buf = jbuf;
             jbuf ^= 1;
         }
 
@@ -537,7 +570,7 @@ constexpr size_t sym_smem_bytes() {
 // Padding bodies sit at +-1e150: d2 stays finite, the refined |d|^-3 underflows to 0 (inf would give
 // inf * 0 = NaN in the refinement).
 // ------------------------------------------------------------------------------------------------
-template <int THREADS, int R, int TILE, int STAGES, int MINB, int UNROLL>
+template <int THREADS, int R, int TILE, int STAGES, int MINB, int UNROLL, int SPLIT = 0>
 __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymParams p) {
     constexpr int IBLK = THREADS * R;
     constexpr int NWARPS = THREADS / 32;
@@ -564,9 +597,10 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
     sym_share(p, share_lo, share_hi);
     const long long total = share_hi - share_lo;
     const long long S = gridDim.x;
-    const long long lo = share_lo + sk_lo(total, blockIdx.x, S), hi = share_lo + sk_lo(total, blockIdx.x + 1, S);
-    if (lo >= hi) { sym_finish(p, total); return; }
-    const int ntiles = (int)(hi - lo);
+    SymRange rg;
+    if (!sym_cta_range<CHUNKS, SPLIT>(share_lo, total, blockIdx.x, S, rg)) { sym_finish(p, total); return; }
+    const long long lo = rg.lo;
+    const int ntiles = (int)(rg.hi - rg.lo);
 
     unsigned long long clk0 = 0, ns0 = 0;
     if (p.clk && blockIdx.x == 0 && tid == 0) {
@@ -622,14 +656,14 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
     // deferred j-side combine, exactly as in the fp32 kernel: arrive on `jbar` when this warp's partials of a
     // tile are written, combine that tile inside the next one after the first ring round; no CTA barrier
     bool jpend = false;
-    int jpend_n = 0, jpend_buf = 0, jbuf = 0;
+    int jpend_lo = 0, jpend_n = 0, jpend_buf = 0, jbuf = 0;
     long long jpend_j0 = 0;
     uint32_t j_parity = 0;
     auto combine_pending = [&]() {
         mbar_wait_warp(jbar, j_parity);
         j_parity ^= 1;
         const double* jb = jpart + (size_t)jpend_buf * NWARPS * 3 * TILE;
-        for (int j = tid; j < jpend_n; j += THREADS) {
+        for (int j = (SPLIT ? jpend_lo : 0) + tid; j < jpend_n; j += THREADS) {
             double ax = 0.0, ay = 0.0, az = 0.0;
 #pragma unroll
             for (int wv = 0; wv < NWARPS; ++wv) {
@@ -678,12 +712,15 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
         const long long j0 = (long long)K * IBLK + (long long)w.t * TILE;
         long long cntl = p.n_total - j0;
         const int jn = cntl > TILE ? TILE : (int)cntl;
+        const int cb = (SPLIT && k == 0) ? rg.c_first : 0;             // SPLIT: this CTA's chunks of the tile, as in the fp32 kernel
+        const int ce = (SPLIT && k == ntiles - 1) ? rg.c_last : CHUNKS;
 
         if (w.c == 0) {
             // diagonal block: ordered, j broadcast from shared memory, self pair masked by index
             const int dj0 = (int)(j0 - ((long long)Ig * IBLK + tid));
+            const int jbeg = cb * 32, jend = (SPLIT && ce * 32 < jn) ? ce * 32 : jn;
 #pragma unroll 2
-            for (int j = 0; j < jn; ++j) {
+            for (int j = jbeg; j < jend; ++j) {
                 const double4 b = tile[j];
                 const int dj = dj0 + j;
 #pragma unroll
@@ -703,11 +740,11 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
         } else {
             double* jp = jpart + ((size_t)jbuf * NWARPS + warp) * 3 * TILE;
 #pragma unroll 1
-            for (int c = 0; c < CHUNKS; ++c) {
+            for (int c = cb; c < ce; ++c) {
                 const int jl = c * 32 + lane;
                 double4 bj = make_double4(-1.0e150, -1.0e150, -1.0e150, 0.0);
                 if (jl < jn) bj = tile[jl];
-                if (c == CHUNKS - 1) {
+                if (c == ce - 1) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty_bar[s]);
                 }
@@ -735,14 +772,14 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
                     jy = __shfl_sync(0xffffffffu, jy, src_lane);
                     jz = __shfl_sync(0xffffffffu, jz, src_lane);
                 }
-                if (c == 0 && jpend) combine_pending();   // previous tile's j side (its buffer is the other one)
+                if (c == cb && jpend) combine_pending();   // previous tile's j side (its buffer is the other one)
                 jp[0 * TILE + jl] = -jx;
                 jp[1 * TILE + jl] = -jy;
                 jp[2 * TILE + jl] = -jz;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(jbar);
-            jpend = true; jpend_n = jn; jpend_j0 = j0; jpend_buf = jbuf;
+            jpend = true; jpend_lo = cb * 32; jpend_n = (SPLIT && ce * 32 < jn) ? ce * 32 : jn; jpend_j0 = j0; jpend_buf = jbuf;
             jbuf ^= 1;
         }
 

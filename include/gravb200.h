@@ -136,7 +136,8 @@ int gravb200_timings(gravb200_ctx* ctx, float* ms, int n);
 /* Introspection used by bench.py / tests: launch geometry and counters.
  * info[0]=grid, [1]=threads, [2]=i-bodies per thread, [3]=j tile, [4]=stages, [5]=dynamic smem bytes,
  * [6]=kernel launches so far, [7]=SM count, [8]=packed f32x2 (1/0), [9]=resident CTAs per SM,
- * [10]=exchange mode (GRAVB200_XCHG_*), [11]=variant id in use. */
+ * [10]=exchange mode (GRAVB200_XCHG_*), [11]=variant id in use, [12]=1 if the symmetric sweep in use cuts its CTA
+ * ranges at chunk granularity (gravb200_set_split). */
 int gravb200_info(const gravb200_ctx* ctx, int64_t* info, int n);
 /* Force a kernel variant (tests / ncu A-B): variant < 0 restores the automatic choice.  Ids 0 .. count-1 are
  * the ordered sweeps (bit-reproducible), ids 100 + k, k < gravb200_sym_variant_count(dtype), the symmetric sweeps
@@ -145,6 +146,13 @@ int gravb200_info(const gravb200_ctx* ctx, int64_t* info, int n);
  * memory (one shard, bit-reproducible; the automatic choice up to 12 800 bodies in float32, 4 736 in float64 —
  * there gravb200_steps(k) is ONE cooperative launch with a grid barrier between the steps). */
 int gravb200_set_variant(gravb200_ctx* ctx, int variant);
+/* Symmetric sweeps only: granularity of the stream-K cut of the flat (block row, j-tile) list into CTA ranges.
+ * mode 0: whole j-tiles (256 / 512 bodies); 1: chunks of 32 j-bodies (two CTAs may share a tile), for the variants
+ * built with that twin; -1 (default): chunks when whole tiles would leave the slowest CTA more than 3 % above the
+ * average — mid-sized universes and small shards, where one tile more or less is a large part of a CTA's work.
+ * Same pairs, same arithmetic per pair; only the grouping of the fp64 atomic adds changes.  Env GRAVB200_SPLIT=0|1
+ * sets the initial mode. */
+int gravb200_set_split(gravb200_ctx* ctx, int mode);
 int gravb200_variant_count(int dtype);
 int gravb200_sym_variant_count(int dtype);
 int gravb200_small_variant_count(void);

@@ -8,7 +8,8 @@
 //   3. the walker enumerates (row, column, tile) in exactly the order of the nested loops and ends at the
 //      end of the last local row, whatever flat offset a CTA starts from (binary search + walk, as in the kernel),
 //   4. the j-tiles of a row cover its column blocks completely (ragged last block included),
-//   5. block rows carry equal work up to one column block (load balance across shards).
+//   5. block rows carry equal work up to one column block (load balance across shards),
+//   6. CTA ranges cut at chunk granularity (sym_cta_range) tile the share's (tile, chunk) items exactly once.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -162,10 +163,52 @@ static void check_shares(long long& cases) {
     }
 }
 
+// CTA ranges at chunk granularity (sym_cta_range<CHUNKS, 1>), replayed the way the kernels use them: tiles [lo, hi)
+// of the share, chunks [c_first, CHUNKS) of the first tile, [0, c_last) of the last one ([c_first, c_last) when they
+// are the same tile).  Every (tile, chunk) of the share belongs to exactly one CTA, no range is empty, the CTAs'
+// chunk counts differ by at most one, and SPLIT = 0 reproduces the whole-tile stream-K ranges.
+template <int CHUNKS>
+static void check_split(long long& cases) {
+    const long long totals[] = {1, 2, 3, 5, 9, 37, 110, 144, 147, 148, 149, 264, 295, 1518, 4224, 22446, 351918};
+    const long long grids[] = {1, 2, 3, 37, 110, 148, 296};
+    const long long share_los[] = {0, 7, 123456};
+    for (long long total : totals)
+        for (long long S : grids)
+            for (long long share_lo : share_los) {
+                ++cases;
+                std::vector<int> seen((size_t)total * CHUNKS, 0);
+                long long cmin = total * CHUNKS, cmax = 0, busy = 0;
+                for (long long b = 0; b < S; ++b) {
+                    SymRange rg, r0;
+                    const bool any0 = sym_cta_range<CHUNKS, 0>(share_lo, total, b, S, r0);
+                    CHECK(any0 == (sk_lo(total, b, S) < sk_lo(total, b + 1, S)), "whole-tile range: emptiness");
+                    if (any0) CHECK(r0.lo == share_lo + sk_lo(total, b, S) && r0.hi == share_lo + sk_lo(total, b + 1, S) && r0.c_first == 0 && r0.c_last == CHUNKS,
+                                    "whole-tile range of CTA %lld (total=%lld S=%lld)", b, total, S);
+                    if (!sym_cta_range<CHUNKS, 1>(share_lo, total, b, S, rg)) continue;
+                    ++busy;
+                    CHECK(rg.lo >= share_lo && rg.hi <= share_lo + total && rg.lo < rg.hi, "tiles [%lld, %lld) outside the share", rg.lo, rg.hi);
+                    CHECK(rg.c_first >= 0 && rg.c_first < CHUNKS && rg.c_last >= 1 && rg.c_last <= CHUNKS, "chunk bounds %d, %d", rg.c_first, rg.c_last);
+                    const int ntiles = (int)(rg.hi - rg.lo);
+                    long long mine = 0;
+                    for (int k = 0; k < ntiles; ++k) {
+                        const int cb = k == 0 ? rg.c_first : 0, ce = k == ntiles - 1 ? rg.c_last : CHUNKS;
+                        CHECK(cb < ce, "empty chunk range [%d, %d) in tile %d of %d (total=%lld S=%lld b=%lld)", cb, ce, k, ntiles, total, S, b);
+                        for (int c = cb; c < ce; ++c) { ++seen[(size_t)(rg.lo - share_lo + k) * CHUNKS + c]; ++mine; }
+                    }
+                    cmin = std::min(cmin, mine); cmax = std::max(cmax, mine);
+                }
+                for (size_t i = 0; i < seen.size(); ++i)
+                    if (seen[i] != 1) { CHECK(false, "chunk %zu of tile %zu visited %d times (total=%lld S=%lld CHUNKS=%d)", i % CHUNKS, i / CHUNKS, seen[i], total, S, CHUNKS); break; }
+                CHECK(busy == std::min<long long>(S, total * CHUNKS), "%lld busy CTAs of %lld for %lld chunks", busy, S, total * CHUNKS);
+                CHECK(cmax - cmin <= 1, "CTA ranges differ by %lld chunks (total=%lld S=%lld)", cmax - cmin, total, S);
+            }
+}
+
 int main() {
     long long cases = 0;
     check_stream_k(cases);
     check_shares(cases);
+    check_split<16>(cases); check_split<8>(cases); check_split<4>(cases);
     sweep<3072, 512>(cases); sweep<3072, 256>(cases); sweep<2048, 512>(cases); sweep<2048, 256>(cases);
     sweep<1024, 256>(cases); sweep<1536, 256>(cases); sweep<1536, 128>(cases); sweep<1024, 128>(cases);
     printf("%s: %lld cases, %lld failed checks\n", fails ? "FAILED" : "OK", cases, fails);

@@ -576,8 +576,10 @@ def test_sass_of_the_default_kernels(shim):
 		ins = funcs[names[0]]
 		return collections.Counter(i.split()[0].split('.')[0] for i in ins), ins
 	for key, must, bars in (
-		('sym_sweep_kernelILi256ELi12ELi512ELi3ELi2E', ('UBLKCP', 'FFMA2', 'FADD2', 'FMUL2', 'MUFU', 'SHFL', 'REDG', 'VOTE'), 6), # fp32 symmetric, variant 100
-		('sym_sweep_kernel_f64ILi256ELi8ELi256ELi3ELi1ELi1E', ('UBLKCP', 'DFMA', 'MUFU', 'SHFL', 'REDG', 'VOTE'), 6), # fp64 symmetric, variant 101
+		('sym_sweep_kernelILi256ELi12ELi512ELi3ELi2ELi0E', ('UBLKCP', 'FFMA2', 'FADD2', 'FMUL2', 'MUFU', 'SHFL', 'REDG', 'VOTE'), 6), # fp32 symmetric, variant 100
+		('sym_sweep_kernelILi256ELi12ELi512ELi3ELi2ELi1E', ('UBLKCP', 'FFMA2', 'FADD2', 'FMUL2', 'MUFU', 'SHFL', 'REDG', 'VOTE'), 6), # its twin with chunk-granular CTA ranges (mid-sized N)
+		('sym_sweep_kernel_f64ILi256ELi8ELi256ELi3ELi1ELi1ELi0E', ('UBLKCP', 'DFMA', 'MUFU', 'SHFL', 'REDG', 'VOTE'), 6), # fp64 symmetric, variant 101
+		('sym_sweep_kernel_f64ILi256ELi8ELi256ELi3ELi1ELi1ELi1E', ('UBLKCP', 'DFMA', 'MUFU', 'SHFL', 'REDG', 'VOTE'), 6), # its chunk-granular twin
 		('sweep_kernelIfLi256ELi8ELi512ELi3ELi1ELi1ELi4ELi1E', ('UBLKCP', 'FFMA2', 'FADD2', 'FMUL2', 'MUFU', 'VOTE'), None), # fp32 ordered, variant 0
 		('sweep_kernelIdLi256ELi2ELi256ELi3ELi2ELi0ELi4ELi0E', ('UBLKCP', 'DFMA', 'MUFU', 'VOTE'), None), # fp64 ordered, variant 0
 		('small_steps_kernelIfLi256ELi4ELi4E', ('UBLKCP', 'FFMA2', 'FADD2', 'FMUL2', 'MUFU', 'VOTE', 'ATOMG', 'SHFL'), None), # fp32 persistent small-N, variant 200
