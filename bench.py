@@ -353,7 +353,7 @@ def config_entry(env, name, log2n, dtype, steps, warmup, parity_rows, sm_max):
 		'config': name, 'n_bodies': run['n'], 'dtype': dtype, 'n_gpus': env.world,
 		'value': run['value'], 'unit': UNIT, 'ms_per_step': run['total_ms'] / steps, 'steps': steps, 'warmup': warmup,
 		'frac_of_pipe_ceiling': frac, 'pipe_ceiling_g_inter_s': ceiling,
-		'kernel': 'symmetric' if symmetric else 'ordered', 'variant': run['info']['variant'], 'grid': run['info']['grid'],
+		'kernel': 'symmetric' if symmetric else 'ordered', 'variant': run['info']['variant'], 'chunk_granular_cta_ranges': bool(run['info'].get('split', 0)), 'grid': run['info']['grid'],
 		'parity': {'max_rel_err_vs_float64': run['parity'], 'rows': run['parity_rows'], 'tolerance': TOLERANCE[dtype],
 			'ok': bool(run['parity'] <= TOLERANCE[dtype])},
 		'clocks': run['clocks'],
@@ -475,7 +475,7 @@ def own_arm(args):
 			'n_bodies': n, 'parallelism': ('row-sharded x%d, %s' % (world, exchange)) if world > 1 else 'single GPU',
 			'exchange': exchange, 'exchange_fallback': e2e.get('exchange_fallback'),
 			'grid': info['grid'], 'threads': info['threads'], 'bodies_per_thread': info['bodies_per_thread'], 'tile': info['tile'],
-			'variant': info['variant'],
+			'variant': info['variant'], 'chunk_granular_cta_ranges': bool(info.get('split', 0)),
 			'l2': 'flushed between timed steps (256 MiB write); the position array is then re-read from L2 by design',
 			'start': 'every timed step starts behind a device-side flag barrier of all ranks (host launch skew is not part of the step)' if world > 1 else 'single stream',
 			},

@@ -273,7 +273,10 @@ const std::vector<SmallVariant>& variants_small() {
     return v;
 }
 constexpr size_t kSmallMaxSmem = 227 * 1024;
-constexpr long long kSmallAutoMaxN = 12800;   // fp32, four row groups per CTA: 94 us at 12288, 106 at 13312 — the symmetric variant 101 takes ~99 us anywhere in 8192 .. 16384
+// Automatic range of the persistent kernel: up to two row groups (64 rows) per CTA in fp32, one in fp64 — 9472 / 4736
+// bodies on 148 SMs.  Beyond, fewer CTAs carry more rows each (N = 9600 fp32: 75 CTAs, 72.7 us per step) and the
+// symmetric sweep with chunk-granular CTA ranges wins (49.0 us; fp64 N = 5000: 40.0 against 49.6; profiles/r02_mid_n.md).
+constexpr int kSmallAutoGroups32 = 2, kSmallAutoGroups64 = 1;
 
 // Rows per shard (contiguous slices of ceil(n / world) rows, the last one short).  The rows
 // a shard OWNS (integrates, keeps velocities of) no longer shape the symmetric sweep: its flat (row, tile) list
@@ -372,7 +375,7 @@ struct gravb200_ctx {
     bool use_sym = false;
     int split_mode = -1;           // CTA ranges of the symmetric sweep at chunk granularity: -1 automatic, 0 never, 1 wherever the variant has the twin
     bool sym_split = false;        // what the current set-up uses
-    long long sym_min_n = 8192;    // automatic choice: symmetric sweep from this N on
+    long long sym_min_n = 4096;    // automatic choice: symmetric sweep from this N on (below, the persistent kernel takes everything it fits)
     int sym_variant = 0, sym_blocks = 0, sym_gblocks = 0;
     long long sym_total = 0, sym_lo = 0, sym_hi = 0;   // flat items of the universe, this shard's share
     // persistent small-N kernel (nbody_small.cuh): geometry, grid barrier counter and its host mirror
@@ -498,7 +501,7 @@ int setup_small(gravb200_ctx* c, int sv, bool forced) {
     const int fit = small_geometry(c->n_total, c->dtype, c->sm_count, v, &g);
     if (fit == 1) return forced ? fail(GRAVB200_EINVAL, "variant %s: %lld bodies need more than %d rows per CTA", v.name, (long long)c->n_total, v.threads) : 1;
     if (fit == 2) return forced ? fail(GRAVB200_EINVAL, "variant %s: %lld bodies do not fit in shared memory (%zu bytes)", v.name, (long long)c->n_total, g.smem) : 1;
-    if (!forced && !(c->dtype == GRAVB200_F32 ? (g.ng <= 2 || (g.ng == 4 && c->n_total <= kSmallAutoMaxN)) : g.ng == 1)) return 1;   // profiles/r02_small_n.jsonl: beyond, the large-N kernels win
+    if (!forced && g.ng > (c->dtype == GRAVB200_F32 ? kSmallAutoGroups32 : kSmallAutoGroups64)) return 1;   // beyond, the symmetric sweep wins
     const void* fn = v.fn[c->dtype == GRAVB200_F32 ? 0 : 1];
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     int occ = 0;
@@ -582,8 +585,8 @@ int pick_variant(gravb200_ctx* c) {
         int sv = -1;
         if (c->forced_variant >= kSymBase) sv = c->forced_variant - kSymBase;
         else if (c->forced_variant < 0 && c->n_total >= c->sym_min_n)
-            sv = c->dtype == GRAVB200_F32 ? (c->n_total >= 65536 ? 0 : (c->n_total > kSmallAutoMaxN ? 1 : 6))
-                                          : (c->n_total >= 10240 ? 1 : 2);   // profiles/r01_sym*_variants_sweep*.txt; fp64 with chunk-granular ranges: r02_split_ab.md
+            sv = c->dtype == GRAVB200_F32 ? (c->n_total >= 65536 ? 0 : (c->n_total >= 9216 ? 1 : 6))
+                                          : (c->n_total >= 10240 ? 1 : 2);   // profiles/r01_sym*_variants_sweep*.txt; with chunk-granular ranges: r02_split_ab.md, r02_mid_n.md
         if (sv >= 0) return setup_sym(c, sv);
     } else if (c->world > 1 && c->peer_mode && c->acc64) {
         int sv = -1;
@@ -1522,9 +1525,14 @@ int gravb200_set_variant(gravb200_ctx* c, int variant) {
     } else if (variant >= (int)variants_of(c->dtype).size()) return fail(GRAVB200_EINVAL, "variant %d out of range", variant);
     if (c->pending) return fail(GRAVB200_EINVAL, "cannot switch variant between stage1 and stage2");
     CU(cudaSetDevice(c->device));
+    const int before = c->forced_variant;
     c->forced_variant = variant < 0 ? -1 : variant;
     int rc = pick_variant(c);
-    if (rc) return rc;
+    if (rc) {   // e.g. a persistent variant the universe does not fit: the context keeps working with what it had
+        c->forced_variant = before;
+        pick_variant(c);
+        return rc;
+    }
     CU(cudaStreamSynchronize(c->stream));
     return 0;
 }

@@ -143,7 +143,7 @@ int gravb200_info(const gravb200_ctx* ctx, int64_t* info, int n);
  * the ordered sweeps (bit-reproducible), ids 100 + k, k < gravb200_sym_variant_count(dtype), the symmetric sweeps
  * (every unordered pair once, fp64 atomics: reproducible up to fp64 rounding of the cross-tile sum), ids 200 + k,
  * k < gravb200_small_variant_count(), the persistent multi-step kernel for universes that fit one SM's shared
- * memory (one shard, bit-reproducible; the automatic choice up to 12 800 bodies in float32, 4 736 in float64 —
+ * memory (one shard, bit-reproducible; the automatic choice up to 9 472 bodies in float32, 4 736 in float64 on 148 SMs —
  * there gravb200_steps(k) is ONE cooperative launch with a grid barrier between the steps). */
 int gravb200_set_variant(gravb200_ctx* ctx, int variant);
 /* Symmetric sweeps only: granularity of the stream-K cut of the flat (block row, j-tile) list into CTA ranges.

@@ -217,7 +217,7 @@ def test_graph_replayed_steps_equal_single_steps(n, variant, dtype, oracle, gpu)
 				sh.steps(k)
 			vid = sh.info()['variant']
 			symmetric = gpu.SYM_BASE <= vid < gpu.SMALL_BASE
-			small_range = n <= (12800 if dtype == 'float32' else 4736) # the automatic range of the persistent kernel on 148 SMs
+			small_range = n <= (9472 if dtype == 'float32' else 4736) # the automatic range of the persistent kernel on 148 SMs (64 / 32 rows per CTA)
 			if vid >= gpu.SMALL_BASE:
 				assert variant < 0 and small_range
 				assert sh.info()['launches'] - launches0 == (k if mode == 'stages' else 1)
@@ -463,7 +463,7 @@ def test_accuracy_command_float32_against_float64(gpu):
 @pytest.mark.parametrize('dtype', DTYPES)
 @pytest.mark.parametrize('n', (12801, 20011, 40000))
 def test_symmetric_sweep_parity_and_reproducibility(n, dtype, oracle, gpu):
-	"""the default path above the persistent small-N kernel's range (N > 12800 fp32): every unordered pair once (nbody_sym.cuh).  Parity against
+	"""the default path above the persistent small-N kernel's range (N > 9472 fp32, > 4736 fp64): every unordered pair once (nbody_sym.cuh).  Parity against
 	the float64 oracle, bit-exact stage 2, and run-to-run agreement (fp64 atomics: reproducible up to the
 	rounding of the cross-tile fp64 sum, far below float32 resolution)"""
 	r, v, m, G, T = oracle.uniform_universe(n, 77, dtype)
@@ -507,8 +507,8 @@ def test_persistent_small_kernel_sizes_and_variants(dtype, oracle, gpu):
 				sh.close()
 				continue
 			sh.set_variant(vid)
-		elif dtype == 'float64' and n > 4736:
-			assert sh.info()['variant'] < gpu.SMALL_BASE # fp64: the automatic range ends at 32 rows per CTA
+		elif n > (9472 if dtype == 'float32' else 4736):
+			assert gpu.SYM_BASE <= sh.info()['variant'] < gpu.SMALL_BASE # the automatic range ends at 64 (fp32) / 32 (fp64) rows per CTA; beyond, the symmetric sweep
 			sh.close()
 			continue
 		assert sh.info()['variant'] >= gpu.SMALL_BASE, (n, vid)
