@@ -643,6 +643,8 @@ def test_symmetric_sweep_on_two_gpus(oracle, gpu):
 	u.add_objects(r, v, m, scale_off = True)
 	u.start()
 	assert all(sh.info()['variant'] >= gpu.SYM_BASE and sh.info()['exchange_mode'] == gpu.XCHG_PEER for sh in u._shards)
+	# a shard's share is 272 tiles for 148 CTAs: chunk-granular CTA ranges inside every shard's share (gravb200_set_split, automatic)
+	assert all(sh.info()['split'] == 1 for sh in u._shards)
 	u.step_stage1()
 	a = np.array(u.accelerations())
 	assert oracle.max_rel_err(a, oracle.stage1_f64(r.astype(np.float32), m.astype(np.float32), G)) <= 1e-4
