@@ -373,6 +373,7 @@ struct gravb200_ctx {
     long long* row_start = nullptr;
     size_t row_start_n = 0;
     bool use_sym = false;
+    bool pdl = false;              // one shard, symmetric step: programmatic dependent launch of the integrate kernel and the next sweep
     int split_mode = -1;           // CTA ranges of the symmetric sweep at chunk granularity: -1 automatic, 0 never, 1 wherever the variant has the twin
     bool sym_split = false;        // what the current set-up uses
     long long sym_min_n = 4096;    // automatic choice: symmetric sweep from this N on (below, the persistent kernel takes everything it fits)
@@ -735,12 +736,21 @@ int launch_sweep(gravb200_ctx* c, int integrate) {
         void* sargs[] = {&sp};
         const bool trace = multi && c->tev[0];
         if (trace) CU(cudaEventRecord(c->tev[0], c->stream));
-        CU(cudaLaunchKernel(c->sym_split ? sv.fn_split : sv.fn, dim3(c->grid), dim3(sv.threads), sargs, sv.smem, c->stream));
+        // one shard: both kernels carry the programmatic-serialization attribute, so each one's launch and prologue
+        // overlap its predecessor's tail (griddep_wait / griddep_launch in the kernels)
+        cudaLaunchAttribute pdl_attr[1];
+        pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t lc;
+        memset(&lc, 0, sizeof(lc));
+        lc.gridDim = dim3(c->grid); lc.blockDim = dim3(sv.threads); lc.dynamicSmemBytes = sv.smem; lc.stream = c->stream;
+        lc.attrs = pdl_attr; lc.numAttrs = (c->pdl && !multi) ? 1 : 0;
+        CU(cudaLaunchKernelExC(&lc, c->sym_split ? sv.fn_split : sv.fn, sargs));
         if (trace) CU(cudaEventRecord(c->tev[1], c->stream));
         const unsigned gb = (unsigned)std::max<long long>(1, (c->n_local + 255) / 256);
-        if (c->dtype == GRAVB200_F32) sym_integrate_kernel<float><<<gb, 256, 0, c->stream>>>(ip);
-        else sym_integrate_kernel<double><<<gb, 256, 0, c->stream>>>(ip);
-        CU(cudaGetLastError());
+        void* iargs[] = {&ip};
+        lc.gridDim = dim3(gb); lc.blockDim = dim3(256); lc.dynamicSmemBytes = 0;
+        CU(cudaLaunchKernelExC(&lc, c->dtype == GRAVB200_F32 ? (const void*)&sym_integrate_kernel<float> : (const void*)&sym_integrate_kernel<double>, iargs));
         if (trace) CU(cudaEventRecord(c->tev[2], c->stream));
         c->sym_tail_pending = multi;
         c->launches += 2;
@@ -1157,6 +1167,7 @@ int gravb200_ctx_create(int64_t n_total, int dtype, int device, int rank, int wo
     c->device = device;
     c->rank = rank;
     c->world = world;
+    if (const char* e = getenv("GRAVB200_PDL")) c->pdl = e[0] == '1';
     if (const char* e = getenv("GRAVB200_SPLIT")) c->split_mode = e[0] == '0' ? 0 : (e[0] == '1' ? 1 : -1);   // A/B runs of unmodified callers
     c->n_total = n_total;
     c->chunk = shard_chunk(n_total, world, dtype);

@@ -172,6 +172,13 @@ __host__ __device__ __forceinline__ long long sk_owner(long long total, long lon
     return ((t + 1) * S - 1) / total;
 }
 
+// Programmatic dependent launch (one shard, symmetric step): the integrate kernel and the next sweep are launched
+// while their predecessor still runs; everything up to griddep_wait() — barrier initialisation, the CTA's range of
+// the tile list, the walk to its first tile — overlaps the predecessor's tail, nothing that depends on the
+// predecessor's results is touched before.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void fence_proxy_async_all() {
     asm volatile("fence.proxy.async;" ::: "memory");
 }

@@ -303,6 +303,8 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
         sym_advance<IBLK, TILE>(pw, p);
         if (++p_slot == STAGES) p_slot = 0;
     };
+    griddep_launch();   // the integrate kernel may be launched now; it waits for this grid to complete before it reads
+    griddep_wait();     // the previous integrate kernel is complete: positions are final, the accumulator is zero
     if (tid == 0) {
         const int pre = ntiles < (STAGES - 1) ? ntiles : (STAGES - 1);
         for (int k = 0; k < pre; ++k) issue_next();
@@ -639,6 +641,8 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
         sym_advance<IBLK, TILE>(pw, p);
         if (++p_slot == STAGES) p_slot = 0;
     };
+    griddep_launch();   // the integrate kernel may be launched now; it waits for this grid to complete before it reads
+    griddep_wait();     // the previous integrate kernel is complete: positions are final, the accumulator is zero
     if (tid == 0) {
         const int pre = ntiles < (STAGES - 1) ? ntiles : (STAGES - 1);
         for (int k = 0; k < pre; ++k) issue_next();
@@ -834,6 +838,8 @@ template <typename REAL>
 __global__ void sym_integrate_kernel(const IntegrateParams q) {
     using V4 = typename Vec4<REAL>::type;
     const long long il = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    griddep_wait();     // this shard's sweep is complete (all its atomic adds are visible)
+    griddep_launch();   // the next sweep may start its prologue; it waits for this grid before it reads positions or adds
     if (q.sync.wait_flags) peer_wait(q.sync);   // every shard's sweep of this step is complete
     if (q.sp.clk && q.sync.wait_flags && blockIdx.x == 0 && threadIdx.x == 0) {   // when the wait ended (gravb200_timings: wait vs work of this kernel)
         unsigned long long t;
