@@ -376,6 +376,9 @@ struct gravb200_ctx {
     bool pdl = false;              // one shard, symmetric step: programmatic dependent launch of the integrate kernel and the next sweep
     int split_mode = -1;           // CTA ranges of the symmetric sweep at chunk granularity: -1 automatic, 0 never, 1 wherever the variant has the twin
     bool sym_split = false;        // what the current set-up uses
+    bool split_weighted = true;    // the twin cuts by cost (diagonal chunks are cheaper), not by chunk count
+    long long sym_cost_lo = 0, sym_cost_hi = 0;   // this shard's share in cost units
+    int sym_w[2] = {4, 3};
     long long sym_min_n = 4096;    // automatic choice: symmetric sweep from this N on (below, the persistent kernel takes everything it fits)
     int sym_variant = 0, sym_blocks = 0, sym_gblocks = 0;
     long long sym_total = 0, sym_lo = 0, sym_hi = 0;   // flat items of the universe, this shard's share
@@ -430,15 +433,25 @@ int setup_sym(gravb200_ctx* c, int sv) {
     // one shard: its block rows are all block rows.  Several shards: every shard walks the GLOBAL list and takes
     // its equal share of it (sym_items), independent of the rows it owns.
     const int nib = Bt;
-    std::vector<long long> rs((size_t)nib + 1, 0);
-    for (int i = 0; i < nib; ++i) rs[i + 1] = rs[i] + sym_row_tiles(c->n_total, iblk, v.tile, Bt, i);
-    if ((size_t)nib + 1 > c->row_start_n) {
+    // rs[0 .. nib]: flat tile offset of every block row; rs[nib + 1 .. 2 nib + 1]: the same prefix in COST units for
+    // the cost-weighted cut of the chunk-granular twins — a chunk (32 j-bodies x one block row) of a diagonal tile is
+    // evaluated ordered and takes ~3/4 (fp32) or ~4/5 (fp64) of a symmetric chunk's time; a row's diagonal tiles come first
+    const int w_sym = c->dtype == GRAVB200_F32 ? 4 : 5, w_diag = c->dtype == GRAVB200_F32 ? 3 : 4;
+    const long long ch = v.tile / 32;
+    std::vector<long long> rs(2 * ((size_t)nib + 1), 0);
+    long long* rc = rs.data() + nib + 1;
+    for (int i = 0; i < nib; ++i) {
+        const long long row_tiles = sym_row_tiles(c->n_total, iblk, v.tile, Bt, i);
+        rs[i + 1] = rs[i] + row_tiles;
+        rc[i + 1] = rc[i] + sym_cost_in_row(c->n_total, iblk, v.tile, i, row_tiles, w_sym, w_diag);
+    }
+    if (rs.size() > c->row_start_n) {
         if (c->row_start) CU(cudaFree(c->row_start));
         c->row_start = nullptr;
-        CU(cudaMalloc(&c->row_start, ((size_t)nib + 1) * sizeof(long long)));
-        c->row_start_n = (size_t)nib + 1;
+        CU(cudaMalloc(&c->row_start, rs.size() * sizeof(long long)));
+        c->row_start_n = rs.size();
     }
-    CU(cudaMemcpyAsync(c->row_start, rs.data(), ((size_t)nib + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->row_start, rs.data(), rs.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));   // rs is a local
     if (!c->acc64) {
         CU(cudaMalloc(&c->acc64, (size_t)c->n_pad * 4 * sizeof(double)));
@@ -463,10 +476,20 @@ int setup_sym(gravb200_ctx* c, int sv) {
     // universes keep the kernel that was profiled.
     const long long share_tiles = c->sym_hi - c->sym_lo, slots = (long long)occ * c->sm_count;
     const long long slowest = (share_tiles + slots - 1) / slots;   // tiles of the slowest CTA with whole-tile ranges
+    // cost of this share and of the slowest CTA with whole-tile ranges (all of its tiles symmetric)
+    auto cost_at = [&](long long t) -> long long {   // cost position of the start of flat tile t
+        if (t >= rs[nib]) return rc[nib];
+        int a = (int)(std::upper_bound(rs.begin(), rs.begin() + nib + 1, t) - rs.begin()) - 1;
+        return rc[a] + sym_cost_in_row(c->n_total, iblk, v.tile, a, t - rs[a], w_sym, w_diag);
+    };
+    c->sym_cost_lo = cost_at(c->sym_lo);
+    c->sym_cost_hi = cost_at(c->sym_hi);
+    c->sym_w[0] = w_sym; c->sym_w[1] = w_diag;
+    const long long share_cost = c->sym_cost_hi - c->sym_cost_lo;
     c->sym_split = v.fn_split != nullptr &&
-                   (c->split_mode == 1 || (c->split_mode < 0 && slowest * slots * 100 > share_tiles * (100 + kSplitGainPct)));
+                   (c->split_mode == 1 || (c->split_mode < 0 && slowest * ch * w_sym * slots * 100 > share_cost * (100 + kSplitGainPct)));
     if (c->sym_split) CU(cudaFuncSetAttribute(v.fn_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
-    const long long units = c->sym_split ? share_tiles * (v.tile / 32) : share_tiles;
+    const long long units = c->sym_split ? share_tiles * ch : share_tiles;
     c->grid = (int)std::max<long long>(1, std::min<long long>(slots, units));
     // several shards with long sweeps (>= 16 tiles per CTA): the shares follow the measured speed of each GPU
     // (nbody_sym.cuh, SymBalance); GRAVB200_BALANCE=0 keeps the equal shares
@@ -685,6 +708,11 @@ int launch_sweep(gravb200_ctx* c, int integrate) {
         sp.clk = c->clk;
         sp.item_lo = c->sym_lo;
         sp.item_hi = c->sym_hi;
+        if (c->sym_split && c->split_weighted && !c->sym_balance) {   // device-computed shares (speed-proportional) keep the count-based cut
+            sp.row_cost = c->row_start + c->sym_blocks + 1;
+            sp.cost_lo = c->sym_cost_lo; sp.cost_hi = c->sym_cost_hi;
+            sp.w_sym = c->sym_w[0]; sp.w_diag = c->sym_w[1];
+        }
         IntegrateParams ip;
         memset(&ip, 0, sizeof(ip));
         ip.sp.pos_front = c->pos[c->front];
@@ -1168,6 +1196,7 @@ int gravb200_ctx_create(int64_t n_total, int dtype, int device, int rank, int wo
     c->rank = rank;
     c->world = world;
     if (const char* e = getenv("GRAVB200_PDL")) c->pdl = e[0] == '1';
+    if (const char* e = getenv("GRAVB200_SPLIT_WEIGHTED")) c->split_weighted = e[0] != '0';
     if (const char* e = getenv("GRAVB200_SPLIT")) c->split_mode = e[0] == '0' ? 0 : (e[0] == '1' ? 1 : -1);   // A/B runs of unmodified callers
     c->n_total = n_total;
     c->chunk = shard_chunk(n_total, world, dtype);

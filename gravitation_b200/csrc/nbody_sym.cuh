@@ -71,6 +71,12 @@ struct SymParams {
     // shards: the GLOBAL list (n_iblocks = n_gblocks, gblock0 = 0, row0 = 0, n_local = n_total) is cut into one
     // equal range per shard — stream-K across GPUs, whatever the row ownership of the integrate step is.
     long long item_lo, item_hi;
+    // chunk-granular CTA ranges (SPLIT twins) cut by COST: a chunk of a diagonal tile (evaluated ordered) is cheaper
+    // than a chunk of a symmetric tile.  row_cost[n_iblocks + 1] = cost prefix per block row (a row's diagonal tiles
+    // come first), [cost_lo, cost_hi) = this launch's share in cost units; nullptr: every chunk counts the same.
+    const long long* row_cost;
+    long long cost_lo, cost_hi;
+    int w_sym, w_diag;
     PeerSync sync;                // several shards: hand-over with the peers' integrate kernels (nbody_kernels.cuh)
     SymBalance bal;               // several shards, long sweeps: speed-proportional shares instead of [item_lo, item_hi)
 };
@@ -224,6 +230,58 @@ __host__ __device__ __forceinline__ bool sym_cta_range(long long share_lo, long 
     return rg.lo < rg.hi;
 }
 
+// Cost of the flat list up to the start of tile `t` of block row `row` (tiles counted within the row; the row's
+// diagonal tiles come first), on top of row_cost[row].  Host (set-up of cost_lo / cost_hi) and device.
+__host__ __device__ inline long long sym_cost_in_row(long long n_total, int iblk, int tile, int Ig, long long tiles_into_row, int w_sym, int w_diag) {
+    const long long nd = sym_tiles_in_block(n_total, iblk, tile, Ig);
+    const int ch = tile / 32;
+    return tiles_into_row < nd ? tiles_into_row * ch * w_diag : nd * ch * w_diag + (tiles_into_row - nd) * ch * w_sym;
+}
+
+// Cost-weighted chunk-granular range of CTA `b` of `S` and the walker position of its first tile.  The share
+// [cost_lo, cost_hi) is cut into S equal cost intervals; a boundary position P maps to the first chunk whose cost
+// interval starts at or after P — the same function for the end of CTA b and the start of CTA b + 1, so the ranges
+// tile the share's chunks exactly once (tests/native/sym_schedule_check.cu).  The two searches run interleaved in
+// one loop: their loads overlap, the prologue pays one dependent chain as before.
+template <int IBLK, int TILE>
+__host__ __device__ inline bool sym_locate_weighted(const SymParams& p, long long b, long long S, SymRange& rg, SymWalker& w0) {
+    constexpr int CH = TILE / 32;
+    const long long span = p.cost_hi - p.cost_lo;
+    const long long P0 = p.cost_lo + sk_lo(span, b, S), P1 = p.cost_lo + sk_lo(span, b + 1, S);
+    if (P0 >= P1) return false;
+    int a0 = 0, b0 = p.n_iblocks, a1 = 0, b1 = p.n_iblocks;   // row_cost[a] <= P < row_cost[b]
+    while (b0 - a0 > 1 || b1 - a1 > 1) {
+        const int m0 = (a0 + b0) >> 1, m1 = (a1 + b1) >> 1;
+        const long long v0 = p.row_cost[m0], v1 = p.row_cost[m1];
+        if (b0 - a0 > 1) { if (v0 <= P0) a0 = m0; else b0 = m0; }
+        if (b1 - a1 > 1) { if (v1 <= P1) a1 = m1; else b1 = m1; }
+    }
+    const long long rc0 = p.row_cost[a0], rc1 = p.row_cost[a1], rs0 = p.row_start[a0], rs1 = p.row_start[a1], rs0n = p.row_start[a0 + 1];
+    auto chunk_in_row = [&](int row, long long r) -> long long {   // r = cost into the row; first chunk starting at or after it
+        const long long nd = (long long)sym_tiles_in_block(p.n_total, IBLK, TILE, p.gblock0 + row) * CH;
+        return r <= nd * p.w_diag ? (r + p.w_diag - 1) / p.w_diag : nd + (r - nd * p.w_diag + p.w_sym - 1) / p.w_sym;
+    };
+    const long long q0 = chunk_in_row(a0, P0 - rc0), q1 = chunk_in_row(a1, P1 - rc1);
+    const long long t0 = rs0 + q0 / CH, t1 = rs1 + q1 / CH;
+    const int c0 = (int)(q0 % CH), c1 = (int)(q1 % CH);
+    if (t0 == t1 && c0 == c1) return false;
+    rg.lo = t0; rg.c_first = c0;
+    rg.hi = c1 ? t1 + 1 : t1; rg.c_last = c1 ? c1 : CH;
+    // walker of tile t0: row a0, or the start of the next row when the boundary fell behind the row's last chunk
+    long long rem = q0 / CH;
+    int a = a0;
+    if (rs0 + rem == rs0n) { ++a; rem = 0; }
+    w0.I = a; w0.c = 0;
+    const int Ig = p.gblock0 + a;
+    for (;;) {
+        const int tb = sym_tiles_in_block(p.n_total, IBLK, TILE, (Ig + w0.c) % p.n_gblocks);
+        if (rem < tb) break;
+        rem -= tb; ++w0.c;
+    }
+    w0.t = (int)rem;
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // THREADS threads, R i-bodies per thread (even), TILE j-bodies per TMA stage (multiple of 32), STAGES.
 // Dynamic shared memory: tile ring | mbarriers (full, empty, jbar) | fp64 i-sums [3][R][THREADS] | j-partials [2][NWARPS][3][TILE].
@@ -260,7 +318,15 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
     const long long total = share_hi - share_lo;
     const long long S = gridDim.x;
     SymRange rg;
-    if (!sym_cta_range<CHUNKS, SPLIT>(share_lo, total, blockIdx.x, S, rg)) { sym_finish(p, total); return; }   // CTA-uniform; an idle CTA still counts as done
+    SymWalker w0;
+    bool located = false;   // range AND first-tile walker already known (cost-weighted cut of the SPLIT twin)
+    if constexpr (SPLIT != 0) {
+        if (p.row_cost) {
+            if (!sym_locate_weighted<IBLK, TILE>(p, blockIdx.x, S, rg, w0)) { sym_finish(p, total); return; }
+            located = true;
+        }
+    }
+    if (!located && !sym_cta_range<CHUNKS, SPLIT>(share_lo, total, blockIdx.x, S, rg)) { sym_finish(p, total); return; }   // CTA-uniform; an idle CTA still counts as done
     const long long lo = rg.lo;
     const int ntiles = (int)(rg.hi - rg.lo);
 
@@ -271,8 +337,7 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
     }
 
     // locate flat item `lo`: block row by binary search over row_start, then walk the column blocks
-    SymWalker w0;
-    {
+    if (!located) {
         int a = 0, b = p.n_iblocks;   // row_start[a] <= lo < row_start[b]
         while (b - a > 1) {
             const int m = (a + b) >> 1;
@@ -600,7 +665,15 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
     const long long total = share_hi - share_lo;
     const long long S = gridDim.x;
     SymRange rg;
-    if (!sym_cta_range<CHUNKS, SPLIT>(share_lo, total, blockIdx.x, S, rg)) { sym_finish(p, total); return; }
+    SymWalker w0;
+    bool located = false;   // as in the fp32 kernel
+    if constexpr (SPLIT != 0) {
+        if (p.row_cost) {
+            if (!sym_locate_weighted<IBLK, TILE>(p, blockIdx.x, S, rg, w0)) { sym_finish(p, total); return; }
+            located = true;
+        }
+    }
+    if (!located && !sym_cta_range<CHUNKS, SPLIT>(share_lo, total, blockIdx.x, S, rg)) { sym_finish(p, total); return; }
     const long long lo = rg.lo;
     const int ntiles = (int)(rg.hi - rg.lo);
 
@@ -610,8 +683,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sym_sweep_kernel_f64(const SymP
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
     }
 
-    SymWalker w0;
-    {
+    if (!located) {
         int a = 0, b = p.n_iblocks;
         while (b - a > 1) {
             const int m = (a + b) >> 1;

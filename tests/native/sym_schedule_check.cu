@@ -9,10 +9,12 @@
 //      end of the last local row, whatever flat offset a CTA starts from (binary search + walk, as in the kernel),
 //   4. the j-tiles of a row cover its column blocks completely (ragged last block included),
 //   5. block rows carry equal work up to one column block (load balance across shards),
-//   6. CTA ranges cut at chunk granularity (sym_cta_range) tile the share's (tile, chunk) items exactly once.
+//   6. CTA ranges cut at chunk granularity (sym_cta_range, and cost-weighted: sym_locate_weighted) tile the share's
+//      (tile, chunk) items exactly once; the weighted ranges carry equal cost and start with the right walker.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #include "../../gravitation_b200/csrc/nbody_sym.cuh"
 
@@ -204,8 +206,79 @@ static void check_split(long long& cases) {
             }
 }
 
+// Cost-weighted chunk-granular ranges (sym_locate_weighted): over the shards' equal shares of the tile list and
+// many grid sizes, the CTAs' chunk ranges tile every share exactly once, the walker a CTA starts with is the
+// nested-loop position of its first tile, and the CTAs' COSTS (diagonal chunks w_diag, symmetric chunks w_sym)
+// differ by less than two symmetric chunks.
+template <int IBLK, int TILE>
+static void check_weighted(long long n, int world, int w_sym, int w_diag, long long& cases) {
+    constexpr int CH = TILE / 32;
+    const int Bt = (int)((n + IBLK - 1) / IBLK);
+    std::vector<long long> rs((size_t)Bt + 1, 0), rc((size_t)Bt + 1, 0);
+    std::vector<SymWalker> order;
+    std::vector<int> is_diag;
+    for (int I = 0; I < Bt; ++I) {
+        const long long row_tiles = sym_row_tiles(n, IBLK, TILE, Bt, I);
+        rs[I + 1] = rs[I] + row_tiles;
+        rc[I + 1] = rc[I] + sym_cost_in_row(n, IBLK, TILE, I, row_tiles, w_sym, w_diag);
+        for (int c = 0; c < sym_ncols(Bt, I); ++c)
+            for (int t = 0; t < sym_tiles_in_block(n, IBLK, TILE, (I + c) % Bt); ++t) { order.push_back({I, c, t}); is_diag.push_back(c == 0); }
+    }
+    const long long total = rs[Bt];
+    CHECK((long long)order.size() == total, "flat size");
+    SymParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_total = n; p.row0 = 0; p.n_local = n; p.n_iblocks = Bt; p.n_gblocks = Bt; p.gblock0 = 0;
+    p.row_start = rs.data(); p.row_cost = rc.data(); p.w_sym = w_sym; p.w_diag = w_diag;
+    auto cost_at = [&](long long t) -> long long {
+        if (t >= total) return rc[Bt];
+        int a = 0, b = Bt;
+        while (b - a > 1) { const int m = (a + b) >> 1; if (rs[m] <= t) a = m; else b = m; }
+        return rc[a] + sym_cost_in_row(n, IBLK, TILE, a, t - rs[a], w_sym, w_diag);
+    };
+    for (long long S : {1LL, 3LL, 37LL, 148LL, 296LL}) {
+        ++cases;
+        std::vector<int> seen((size_t)total * CH, 0);
+        for (int rank = 0; rank < world; ++rank) {
+            const long long lo = sk_lo(total, rank, world), hi = sk_lo(total, rank + 1, world);
+            p.item_lo = lo; p.item_hi = hi; p.cost_lo = cost_at(lo); p.cost_hi = cost_at(hi);
+            long long cmin = -1, cmax = -1;
+            for (long long b = 0; b < S; ++b) {
+                SymRange rg; SymWalker w0;
+                if (!sym_locate_weighted<IBLK, TILE>(p, b, S, rg, w0)) continue;
+                CHECK(rg.lo >= lo && rg.hi <= hi && rg.lo < rg.hi, "tiles [%lld, %lld) outside the share [%lld, %lld)", rg.lo, rg.hi, lo, hi);
+                const SymWalker& e = order[(size_t)rg.lo];
+                CHECK(w0.I == e.I && w0.c == e.c && w0.t == e.t, "walker (%d,%d,%d) != (%d,%d,%d) at tile %lld (n=%lld S=%lld)", w0.I, w0.c, w0.t, e.I, e.c, e.t, rg.lo, n, S);
+                const int ntiles = (int)(rg.hi - rg.lo);
+                long long cost = 0;
+                for (int k = 0; k < ntiles; ++k) {
+                    const int cb = k == 0 ? rg.c_first : 0, ce = k == ntiles - 1 ? rg.c_last : CH;
+                    CHECK(cb < ce, "empty chunk range [%d, %d) (n=%lld S=%lld b=%lld)", cb, ce, n, S, b);
+                    for (int c = cb; c < ce; ++c) { ++seen[(size_t)(rg.lo + k) * CH + c]; cost += is_diag[(size_t)(rg.lo + k)] ? w_diag : w_sym; }
+                }
+                if (cmin < 0 || cost < cmin) cmin = cost;
+                if (cost > cmax) cmax = cost;
+            }
+            if ((hi - lo) * CH >= S) CHECK(cmax - cmin < 2 * w_sym, "CTA costs differ by %lld (n=%lld iblk=%d S=%lld world=%d rank=%d)", cmax - cmin, n, IBLK, S, world, rank);
+        }
+        for (size_t i = 0; i < seen.size(); ++i)
+            if (seen[i] != 1) { CHECK(false, "chunk %zu of tile %zu visited %d times (n=%lld iblk=%d tile=%d S=%lld world=%d)", i % CH, i / CH, seen[i], n, IBLK, TILE, S, world); break; }
+    }
+}
+
+template <int IBLK, int TILE>
+static void sweep_weighted(long long& cases) {
+    const long long sizes[] = {1, 33, TILE + 1, IBLK - 1, IBLK, IBLK + 1, 2LL * IBLK + 5, 5000, 9600, 12001, 16384, 24576, 40000, 65536, 100003};
+    for (long long n : sizes)
+        for (int world : {1, 2, 8}) {
+            check_weighted<IBLK, TILE>(n, world, 4, 3, cases);
+            check_weighted<IBLK, TILE>(n, world, 5, 4, cases);
+        }
+}
+
 int main() {
     long long cases = 0;
+    sweep_weighted<3072, 512>(cases); sweep_weighted<2048, 512>(cases); sweep_weighted<2048, 256>(cases); sweep_weighted<1024, 256>(cases); sweep_weighted<1024, 128>(cases);
     check_stream_k(cases);
     check_shares(cases);
     check_split<16>(cases); check_split<8>(cases); check_split<4>(cases);
