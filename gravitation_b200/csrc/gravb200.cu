@@ -436,7 +436,11 @@ int setup_sym(gravb200_ctx* c, int sv) {
     // rs[0 .. nib]: flat tile offset of every block row; rs[nib + 1 .. 2 nib + 1]: the same prefix in COST units for
     // the cost-weighted cut of the chunk-granular twins — a chunk (32 j-bodies x one block row) of a diagonal tile is
     // evaluated ordered and takes ~3/4 (fp32) or ~4/5 (fp64) of a symmetric chunk's time; a row's diagonal tiles come first
-    const int w_sym = c->dtype == GRAVB200_F32 ? 4 : 5, w_diag = c->dtype == GRAVB200_F32 ? 3 : 4;
+    int w_sym = c->dtype == GRAVB200_F32 ? 4 : 5, w_diag = c->dtype == GRAVB200_F32 ? 3 : 4;
+    if (const char* e = getenv("GRAVB200_SPLIT_W")) {   // "w_sym,w_diag": tuning sweeps (scripts/weighted_ab.py)
+        int a = 0, b = 0;
+        if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && b >= 1 && a <= 64 && b <= 64) { w_sym = a; w_diag = b; }
+    }
     const long long ch = v.tile / 32;
     std::vector<long long> rs(2 * ((size_t)nib + 1), 0);
     long long* rc = rs.data() + nib + 1;
@@ -708,7 +712,11 @@ int launch_sweep(gravb200_ctx* c, int integrate) {
         sp.clk = c->clk;
         sp.item_lo = c->sym_lo;
         sp.item_hi = c->sym_hi;
-        if (c->sym_split && c->split_weighted && !c->sym_balance) {   // device-computed shares (speed-proportional) keep the count-based cut
+        // device-computed shares (speed-proportional) keep the count-based cut; so do the R = 4 fp64 variants, whose
+        // diagonal chunks are no cheaper than their symmetric ones (N = 7000: 55.5 us by count, 59.7 weighted 5:4;
+        // the R = 8 variant at 12 288: 136.4 -> 125.6; fp32 R = 8, 4:3: 64.9 -> 62.0 at 12 288, +-0.5 % elsewhere;
+        // profiles/r02_weighted_scan*.jsonl)
+        if (c->sym_split && c->split_weighted && !c->sym_balance && (c->dtype == GRAVB200_F32 || sv.r >= 8)) {
             sp.row_cost = c->row_start + c->sym_blocks + 1;
             sp.cost_lo = c->sym_cost_lo; sp.cost_hi = c->sym_cost_hi;
             sp.w_sym = c->sym_w[0]; sp.w_diag = c->sym_w[1];

@@ -509,6 +509,9 @@ __global__ void __launch_bounds__(THREADS, 1) sym_sweep_kernel(const SymParams p
             if (jbeg == 0 && jend == TILE) {
 #pragma unroll 2
                 for (int j = 0; j < TILE; ++j) ordered(tile[j], dj0 + j);
+            } else if (SPLIT) {   // partial diagonal tiles are the rule with chunk-granular ranges, not the ragged exception
+#pragma unroll 2
+                for (int j = jbeg; j < jend; ++j) ordered(tile[j], dj0 + j);
             } else {
 #pragma unroll 1
                 for (int j = jbeg; j < jend; ++j) ordered(tile[j], dj0 + j);
