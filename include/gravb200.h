@@ -150,8 +150,10 @@ int gravb200_set_variant(gravb200_ctx* ctx, int variant);
  * mode 0: whole j-tiles (256 / 512 bodies); 1: chunks of 32 j-bodies (two CTAs may share a tile), for the variants
  * built with that twin; -1 (default): chunks when whole tiles would leave the slowest CTA more than 3 % above the
  * average — mid-sized universes and small shards, where one tile more or less is a large part of a CTA's work.
- * Same pairs, same arithmetic per pair; only the grouping of the fp64 atomic adds changes.  Env GRAVB200_SPLIT=0|1
- * sets the initial mode. */
+ * Same pairs, same arithmetic per pair; only the grouping of the fp64 atomic adds changes.  With chunks the ranges
+ * carry equal COST (a chunk of a diagonal tile, evaluated ordered, weighs 3/4 of a symmetric one in float32, 4/5 in
+ * float64 with 8 rows per thread; GRAVB200_SPLIT_WEIGHTED=0: equal chunk counts).  Env GRAVB200_SPLIT=0|1 sets the
+ * initial mode. */
 int gravb200_set_split(gravb200_ctx* ctx, int mode);
 int gravb200_variant_count(int dtype);
 int gravb200_sym_variant_count(int dtype);
