@@ -18,7 +18,9 @@
 // (self pair masked by index, as in the ordered kernel) and, symmetrically, the column blocks I+1 .. I+H
 // (cyclically, H = half of the other blocks), so every block row carries the same amount of work whatever
 // rank owns it and every unordered pair of blocks is visited exactly once.  The flat list of (row, tile)
-// items is cut stream-K style into equal ranges, one per CTA.  Partial accelerations of both sides are
+// items is cut stream-K style into equal ranges, one per CTA — at whole tiles (SPLIT = 0, the large universes) or
+// at 32-body chunks of equal cost (SPLIT = 1 twins: mid-sized universes and small shards, where a CTA holds only
+// a few tiles; sym_cta_range / sym_locate_weighted).  Partial accelerations of both sides are
 // added into a global fp64 accumulator with RED.ADD.F64; `integrate_kernel` (O(N)) turns the accumulator
 // into a, v', r'.  The fp64 sums of fp32 tile partials are exact unless the partials of one body span
 // more than 2^29 in magnitude, so results are reproducible up to that rounding, not by construction.
