@@ -259,7 +259,7 @@ static void check_weighted(long long n, int world, int w_sym, int w_diag, long l
                 if (cmin < 0 || cost < cmin) cmin = cost;
                 if (cost > cmax) cmax = cost;
             }
-            if ((hi - lo) * CH >= S) CHECK(cmax - cmin < 2 * w_sym, "CTA costs differ by %lld (n=%lld iblk=%d S=%lld world=%d rank=%d)", cmax - cmin, n, IBLK, S, world, rank);
+            if ((hi - lo) * CH >= S) CHECK(cmax - cmin < 2 * std::max(w_sym, w_diag), "CTA costs differ by %lld (n=%lld iblk=%d S=%lld world=%d rank=%d)", cmax - cmin, n, IBLK, S, world, rank);
         }
         for (size_t i = 0; i < seen.size(); ++i)
             if (seen[i] != 1) { CHECK(false, "chunk %zu of tile %zu visited %d times (n=%lld iblk=%d tile=%d S=%lld world=%d)", i % CH, i / CH, seen[i], n, IBLK, TILE, S, world); break; }
